@@ -1,0 +1,1023 @@
+// b2s C-ABI implementation (include/b2s.h): engine / band objects, kernel launches, host tracker glue.
+// The compute path is CUDA only; there is deliberately no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2s.h"
+#include "detect.cuh"
+#include "host_utils.h"
+#include "spectral.cuh"
+#include "tracker.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t err__ = (call);                                                                         \
+    if (err__ != cudaSuccess) return fail(B2S_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) return fail(B2S_E_NOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    if (cudaMallocHost(&p, count * sizeof(T)) != cudaSuccess) return fail(B2S_E_NOMEM, "cudaMallocHost of %zu bytes failed", count * sizeof(T));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+void make_window(const b2s_band_config& cfg, std::vector<float>& w) {
+  const int n = cfg.fft_size;
+  w.resize(n);
+  if (cfg.window_kind == B2S_WINDOW_USER && cfg.window_taps) {
+    std::memcpy(w.data(), cfg.window_taps, sizeof(float) * n);
+  } else {
+    // gr::fft::window::hamming(N) (reference call site sources/radio/sdr_device.cpp:164): symmetric, double -> f32
+    const double m = static_cast<double>(n - 1);
+    for (int i = 0; i < n; ++i) w[i] = (n == 1) ? 1.0f : static_cast<float>(0.54 - 0.46 * std::cos((2.0 * M_PI * i) / m));
+  }
+}
+
+}  // namespace
+
+using namespace b2s;
+
+// ------------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------------
+struct b2s_engine {
+  int device = 0;
+  cudaDeviceProp prop{};
+  int sm_count = 0;
+};
+
+// K1 launcher -------------------------------------------------------------------------------------------------
+namespace {
+
+template <int N, int MODE>
+int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+  using PL = FftPlanT<N>;
+  constexpr int T = N / PL::E;
+  const size_t smem = sizeof(float2) * exchange_elems<N>() + (MODE == kModeCs8Tma ? 2 * N : 0);
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(k_spectrum<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum<N, MODE>, T, smem));
+    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum<%d> does not fit on an SM", N);
+    configured = true;
+  }
+  const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
+  k_spectrum<N, MODE><<<grid, T, smem, stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int MODE>
+int launch_spectrum_n(const b2s_engine* e, int n, const SpectralArgs& a, cudaStream_t stream) {
+  switch (n) {
+    case 256: return launch_spectrum_t<256, MODE>(e, a, stream);
+    case 512: return launch_spectrum_t<512, MODE>(e, a, stream);
+    case 1024: return launch_spectrum_t<1024, MODE>(e, a, stream);
+    case 2048: return launch_spectrum_t<2048, MODE>(e, a, stream);
+    case 4096: return launch_spectrum_t<4096, MODE>(e, a, stream);
+    case 8192: return launch_spectrum_t<8192, MODE>(e, a, stream);
+    case 16384: return launch_spectrum_t<16384, MODE>(e, a, stream);
+    default: return fail(B2S_E_INVALID, "fft_size %d is not supported (256..16384)", n);
+  }
+}
+
+int launch_spectrum(const b2s_engine* e, int n, int iq_format, const SpectralArgs& a, cudaStream_t stream) {
+  if (iq_format == B2S_IQ_CF32) return launch_spectrum_n<kModeCf32>(e, n, a, stream);
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.iq) % 16 == 0) && (a.frame_stride_bytes % 16 == 0);
+  if (aligned) return launch_spectrum_n<kModeCs8Tma>(e, n, a, stream);
+  return launch_spectrum_n<kModeCs8Direct>(e, n, a, stream);
+}
+
+struct SpectralTables {
+  DevBuf<float> wscale;
+  DevBuf<float2> twiddle;
+  int build(const b2s_band_config& cfg) {
+    const int n = cfg.fft_size;
+    std::vector<float> w;
+    make_window(cfg, w);
+    if (cfg.iq_format == B2S_IQ_CS8) {
+      // unpack scale folded into the window: x*scale*w -> x*(scale*w); differs from the two-step product by < 1 ulp
+      for (int i = 0; i < n; ++i) w[i] = w[i] * cfg.iq_scale;
+    }
+    std::vector<float2> tw(n);
+    for (int j = 0; j < n; ++j) {
+      const double ang = -2.0 * M_PI * j / n;
+      tw[j] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+    }
+    int rc = wscale.alloc(n);
+    if (rc) return rc;
+    rc = twiddle.alloc(n);
+    if (rc) return rc;
+    CU(cudaMemcpy(wscale.p, w.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(twiddle.p, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    return 0;
+  }
+  void release() {
+    wscale.release();
+    twiddle.release();
+  }
+};
+
+int validate_config(const b2s_band_config& c) {
+  if (!is_pow2(c.fft_size) || c.fft_size < 256 || c.fft_size > 16384) return fail(B2S_E_INVALID, "fft_size must be a power of two in 256..16384 (got %d)", c.fft_size);
+  if (c.sample_rate_hz <= 0) return fail(B2S_E_INVALID, "sample_rate_hz must be positive");
+  if (c.frame_stride_samples < c.fft_size) return fail(B2S_E_INVALID, "frame_stride_samples (%d) < fft_size", c.frame_stride_samples);
+  if (c.iq_format != B2S_IQ_CS8 && c.iq_format != B2S_IQ_CF32) return fail(B2S_E_INVALID, "unknown iq_format %d", c.iq_format);
+  if (c.window_kind == B2S_WINDOW_USER && !c.window_taps) return fail(B2S_E_INVALID, "window_taps is NULL");
+  if (c.grouping_x < 1 || c.grouping_x > 65) return fail(B2S_E_INVALID, "grouping_x must be in 1..65");
+  if (c.grouping_y < 1 || c.grouping_y > 256) return fail(B2S_E_INVALID, "grouping_y must be in 1..256");
+  if (c.group_size_bins < 0 || c.group_size_bins > 4096) return fail(B2S_E_INVALID, "group_size_bins must be in 0..4096");
+  if (c.learn_frames < 1) return fail(B2S_E_INVALID, "learn_frames must be >= 1");
+  if (c.n_ignored < 0 || c.n_ignored > B2S_MAX_IGNORED) return fail(B2S_E_INVALID, "n_ignored out of range");
+  if (c.tuning_step_hz <= 0) return fail(B2S_E_INVALID, "tuning_step_hz must be positive");
+  if (c.spectrogram_out_size < 0 || (c.spectrogram_out_size > 0 && (!is_pow2(c.spectrogram_out_size) || c.spectrogram_out_size > c.fft_size ||
+                                                                   c.fft_size / c.spectrogram_out_size > kDetectBinsPerCta)))
+    return fail(B2S_E_INVALID, "spectrogram_out_size must be 0 or a power of two with N/out <= %d", kDetectBinsPerCta);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// band
+// ------------------------------------------------------------------------------------------------------------
+struct NoiseSlot {
+  DevBuf<float> threshold;
+  int samples = 0;
+  bool ready = false;
+};
+struct SpectroSlot {
+  DevBuf<float> sum;
+  int counter = 0;
+  int64_t last_send = 0;
+};
+struct SentRow {
+  int64_t time;
+  int32_t center;
+  std::vector<int8_t> row;
+};
+
+struct b2s_band : public DeviceQueries {
+  b2s_engine* engine = nullptr;
+  b2s_band_config cfg{};
+  std::mutex mutex;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int max_frames = 0;
+  int entry_capacity = 0;
+
+  SpectralTables tables;
+  DevBuf<unsigned char> d_iq;
+  DevBuf<float> d_psd, d_lin, d_dense_q, d_dense_avg, d_dense_box;
+  DevBuf<int> d_peak_idx;
+  DevBuf<float> d_peak_val;
+  DevBuf<float> d_sum, d_ring[2], d_avg_last, d_ckpt;
+  int ring_cur = 0;  // d_ring[ring_cur] = current ring; the other one = ring as it was before the last push
+  int avg_frames = 0;
+  DevBuf<DetectEntry> d_entries;
+  DevBuf<int> d_entry_count;
+  DevBuf<int> d_spec_slot, d_spec_div;
+  DevBuf<signed char> d_spec_rows;
+  DevBuf<WindowWork> d_work;
+  DevBuf<float> d_wq_val;
+  DevBuf<int> d_wq_idx;
+  PinBuf<DetectEntry> h_entries;
+  PinBuf<int> h_small;
+
+  std::map<int32_t, NoiseSlot> noise;
+  std::map<int32_t, SpectroSlot> spectro;
+  std::vector<SentRow> sent;
+  int32_t center = 0;
+  Tracker tracker;
+
+  // context of the push being processed (for DeviceQueries)
+  int cur_frames = 0;
+  int cur_noise_samples = 0;
+  std::vector<float> thr_host;
+  bool thr_host_valid = false;
+  std::vector<float> scratch;
+
+  ~b2s_band() {
+    tables.release();
+    d_iq.release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
+    d_peak_idx.release(); d_peak_val.release(); d_sum.release(); d_ring[0].release(); d_ring[1].release(); d_avg_last.release();
+    d_ckpt.release(); d_entries.release(); d_entry_count.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
+    d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
+    for (auto& kv : noise) kv.second.threshold.release();
+    for (auto& kv : spectro) kv.second.sum.release();
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  bool learning_frame(int t) const { return cur_noise_samples + t < cfg.learn_frames; }
+
+  int noise_slot(NoiseSlot** out) {
+    auto it = noise.find(center);
+    if (it == noise.end()) {
+      it = noise.emplace(center, NoiseSlot{}).first;
+      int rc = it->second.threshold.alloc(cfg.fft_size);
+      if (rc) return rc;
+      std::vector<float> init(cfg.fft_size, -std::numeric_limits<float>::max());  // noise_learner.cpp:16
+      CU(cudaMemcpyAsync(it->second.threshold.p, init.data(), sizeof(float) * cfg.fft_size, cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+    }
+    *out = &it->second;
+    return 0;
+  }
+
+  int ensure_threshold_on_host() {
+    if (thr_host_valid) return 0;
+    NoiseSlot* ns = nullptr;
+    int rc = noise_slot(&ns);
+    if (rc) return rc;
+    thr_host.resize(cfg.fft_size);
+    CU(cudaMemcpyAsync(thr_host.data(), ns->threshold.p, sizeof(float) * cfg.fft_size, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    thr_host_valid = true;
+    return 0;
+  }
+
+  // ---- DeviceQueries ----
+  int fetch_ring_window(int frame_first, int rows, int bin_lo, int width, float* out) override {
+    const int n = cfg.fft_size, Y = cfg.grouping_y;
+    int rc = ensure_threshold_on_host();
+    if (rc) return rc;
+    const float* ring_before = d_ring[ring_cur ^ 1].p;  // ring as it was when this push began
+    for (int r = 0; r < rows; ++r) {
+      const int f = frame_first + r;
+      float* dst = out + static_cast<size_t>(r) * width;
+      if (f >= 0) {
+        CU(cudaMemcpyAsync(dst, d_psd.p + static_cast<size_t>(f) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, stream));
+      } else {
+        const int row = Y + f;  // f = -1 is the newest pre-push row
+        if (row < 0) {
+          for (int i = 0; i < width; ++i) dst[i] = 0.0f;  // cannot happen: rows <= Y
+        } else {
+          CU(cudaMemcpyAsync(dst, ring_before + static_cast<size_t>(row) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, stream));
+        }
+      }
+    }
+    CU(cudaStreamSynchronize(stream));
+    for (int r = 0; r < rows; ++r) {
+      const int f = frame_first + r;
+      if (f < 0) continue;
+      float* dst = out + static_cast<size_t>(r) * width;
+      if (learning_frame(f)) {
+        for (int i = 0; i < width; ++i) dst[i] = kNoData;
+      } else {
+        for (int i = 0; i < width; ++i) dst[i] = dst[i] - thr_host[bin_lo + i];  // same IEEE subtraction as the kernel
+      }
+    }
+    return 0;
+  }
+
+  int query_windows(const std::vector<Window>& w, std::vector<std::vector<float>>& values, std::vector<std::vector<int>>& indices) override {
+    std::vector<WindowWork> work;
+    std::vector<int> offset(w.size());
+    int total = 0;
+    int max_width = 0;
+    const int half = cfg.grouping_x / 2;
+    for (size_t q = 0; q < w.size(); ++q) {
+      offset[q] = total;
+      for (int f = w[q].frame_lo; f < w[q].frame_hi;) {
+        const int end = std::min(w[q].frame_hi, (f / kCheckpointEvery + 1) * kCheckpointEvery);
+        work.push_back(WindowWork{w[q].bin_lo, w[q].bin_hi, f, end, total + (f - w[q].frame_lo)});
+        f = end;
+      }
+      total += w[q].frame_hi - w[q].frame_lo;
+      max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half);
+    }
+    int rc = d_work.alloc(work.size());
+    if (rc) return rc;
+    if ((rc = d_wq_val.alloc(total))) return rc;
+    if ((rc = d_wq_idx.alloc(total))) return rc;
+    CU(cudaMemcpyAsync(d_work.p, work.data(), sizeof(WindowWork) * work.size(), cudaMemcpyHostToDevice, stream));
+    NoiseSlot* ns = nullptr;
+    if ((rc = noise_slot(&ns))) return rc;
+    WindowArgs a{};
+    a.n = cfg.fft_size;
+    a.group_y = cfg.grouping_y;
+    a.group_x = cfg.grouping_x;
+    a.psd = d_psd.p;
+    a.threshold = ns->threshold.p;
+    a.noise_samples = cur_noise_samples;
+    a.learn_frames = cfg.learn_frames;
+    a.ring_in = d_ring[ring_cur ^ 1].p;
+    a.avg_frames = cur_avg_frames_before;
+    a.checkpoints = d_ckpt.p;
+    a.work = d_work.p;
+    a.out_value = d_wq_val.p;
+    a.out_index = d_wq_idx.p;
+    const size_t smem = sizeof(float) * 2 * max_width;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_window_query, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k_window_query<<<static_cast<unsigned>(work.size()), 256, smem, stream>>>(a);
+    CU(cudaGetLastError());
+    std::vector<float> v(total);
+    std::vector<int> ix(total);
+    CU(cudaMemcpyAsync(v.data(), d_wq_val.p, sizeof(float) * total, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(ix.data(), d_wq_idx.p, sizeof(int) * total, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    values.resize(w.size());
+    indices.resize(w.size());
+    for (size_t q = 0; q < w.size(); ++q) {
+      const int len = w[q].frame_hi - w[q].frame_lo;
+      values[q].assign(v.begin() + offset[q], v.begin() + offset[q] + len);
+      indices[q].assign(ix.begin() + offset[q], ix.begin() + offset[q] + len);
+    }
+    return 0;
+  }
+  int cur_avg_frames_before = 0;
+
+  int init(b2s_engine* e, const b2s_band_config& c) {
+    engine = e;
+    cfg = c;
+    CU(cudaSetDevice(e->device));
+    max_frames = c.max_frames_per_push > 0 ? c.max_frames_per_push : 4096;
+    entry_capacity = c.detect_capacity > 0 ? c.detect_capacity : max_frames * 64;
+    center = c.center_hz;
+    CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+    int rc = tables.build(c);
+    if (rc) return rc;
+    cfg.window_taps = nullptr;
+    const size_t n = c.fft_size, Y = c.grouping_y;
+    if ((rc = d_psd.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+    if ((rc = d_peak_idx.alloc(max_frames))) return rc;
+    if ((rc = d_peak_val.alloc(max_frames))) return rc;
+    if ((rc = d_sum.alloc(n))) return rc;
+    if ((rc = d_ring[0].alloc(Y * n))) return rc;
+    if ((rc = d_ring[1].alloc(Y * n))) return rc;
+    if ((rc = d_avg_last.alloc(n))) return rc;
+    if ((rc = d_ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
+    if ((rc = d_entries.alloc(entry_capacity))) return rc;
+    if ((rc = d_entry_count.alloc(1))) return rc;
+    if ((rc = d_spec_slot.alloc(max_frames))) return rc;
+    if ((rc = h_small.alloc(max_frames + 64))) return rc;
+    if ((rc = h_entries.alloc(entry_capacity))) return rc;
+    rc = reset_averager();
+    if (rc) return rc;
+    // tracker parameters
+    TrackerParams& p = tracker.p;
+    p.n = c.fft_size;
+    p.sample_rate = c.sample_rate_hz;
+    p.center = c.center_hz;
+    p.range_lo = c.range_lo_hz;
+    p.range_hi = c.range_hi_hz;
+    p.n_ignored = c.n_ignored;
+    for (int i = 0; i < c.n_ignored; ++i) {
+      p.ignored_lo[i] = c.ignored_lo_hz[i];
+      p.ignored_hi[i] = c.ignored_hi_hz[i];
+    }
+    p.group_size = c.group_size_bins;
+    p.group_y = c.grouping_y;
+    p.start_level = c.start_level;
+    p.stop_level = c.stop_level;
+    p.tuning_step = c.tuning_step_hz;
+    p.min_time = c.min_time_ms;
+    p.timeout = c.timeout_ms;
+    p.max_time = c.max_time_ms;
+    return 0;
+  }
+
+  // Averager::reset (averager.cpp:27-34) / constructor state (averager.cpp:7-12)
+  int reset_averager() {
+    const size_t n = cfg.fft_size, Y = cfg.grouping_y;
+    CU(cudaMemsetAsync(d_sum.p, 0, sizeof(float) * n, stream));
+    CU(cudaMemsetAsync(d_ring[0].p, 0, sizeof(float) * Y * n, stream));
+    CU(cudaMemsetAsync(d_ring[1].p, 0, sizeof(float) * Y * n, stream));
+    std::vector<float> nd(n, kNoData);
+    CU(cudaMemcpyAsync(d_avg_last.p, nd.data(), sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    avg_frames = 0;
+    ring_cur = 0;
+    return 0;
+  }
+
+  int push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out);
+};
+
+int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
+  const int n = cfg.fft_size, Y = cfg.grouping_y;
+  const int T = static_cast<int>(frames);
+  const size_t bytes_per_sample = cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
+  const bool want_dense_q = out && out->noise_sub_db, want_dense_avg = out && out->avg_db, want_dense_box = out && out->box_db;
+  int rc;
+  if (want_dense_q && (rc = d_dense_q.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+  if (want_dense_avg && (rc = d_dense_avg.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+  if (want_dense_box && (rc = d_dense_box.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+
+  // ---- K1: spectra ----
+  SpectralArgs sa{};
+  sa.iq = iq_dev;
+  sa.frame_stride_bytes = static_cast<long long>(cfg.frame_stride_samples) * bytes_per_sample;
+  sa.n_frames = T;
+  sa.wscale = tables.wscale.p;
+  sa.twiddle = tables.twiddle.p;
+  sa.inv_fs = 1.0f / static_cast<float>(cfg.sample_rate_hz);
+  sa.psd_db = d_psd.p;
+  sa.power_lin = nullptr;
+  sa.peak_index = d_peak_idx.p;
+  sa.peak_value = d_peak_val.p;
+  if ((rc = launch_spectrum(engine, n, cfg.iq_format, sa, stream))) return rc;
+
+  // ---- plan the spectrogram emissions of this chunk from the clock (Spectrogram::send, spectrogram.cpp:62-75) ----
+  int n_slots = 0;
+  SpectroSlot* ss = nullptr;
+  const int M = cfg.spectrogram_out_size;
+  std::vector<int64_t> slot_time;
+  if (M > 0) {
+    auto it = spectro.find(center);
+    if (it == spectro.end()) {
+      it = spectro.emplace(center, SpectroSlot{}).first;
+      if ((rc = it->second.sum.alloc(M))) return rc;
+      CU(cudaMemsetAsync(it->second.sum.p, 0, sizeof(float) * M, stream));
+      it->second.counter = 0;  // the reference leaves m_counter uninitialised (spectrogram.cpp:9); defined as 0
+      it->second.last_send = host::frame_time(t0_ms, period_ms, frame_offset);  // Container ctor: getTime()
+    }
+    ss = &it->second;
+    int* slots = h_small.p;
+    std::vector<int> divs;
+    for (int t = 0; t < T; ++t) {
+      const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
+      ss->counter++;
+      if (ss->last_send + cfg.spectrogram_interval_ms < now) {
+        slots[t] = n_slots++;
+        divs.push_back(ss->counter);
+        slot_time.push_back(now);
+        ss->counter = 0;
+        ss->last_send = now;
+      } else {
+        slots[t] = -1;
+      }
+    }
+    CU(cudaMemcpyAsync(d_spec_slot.p, slots, sizeof(int) * T, cudaMemcpyHostToDevice, stream));
+    if (n_slots > 0) {
+      if ((rc = d_spec_div.alloc(n_slots))) return rc;
+      if ((rc = d_spec_rows.alloc(static_cast<size_t>(n_slots) * M))) return rc;
+      CU(cudaMemcpyAsync(d_spec_div.p, divs.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));  // divs is a local vector
+    }
+  }
+
+  // ---- K2: noise / averager / boxcar / detect / spectrogram ----
+  NoiseSlot* ns = nullptr;
+  if ((rc = noise_slot(&ns))) return rc;
+  CU(cudaMemsetAsync(d_entry_count.p, 0, sizeof(int), stream));
+  DetectArgs da{};
+  da.n = n;
+  da.n_frames = T;
+  da.group_y = Y;
+  da.group_x = cfg.grouping_x;
+  da.psd = d_psd.p;
+  da.threshold = ns->threshold.p;
+  da.noise_samples = ns->ready ? cfg.learn_frames : ns->samples;
+  da.learn_frames = cfg.learn_frames;
+  da.avg_sum = d_sum.p;
+  da.ring_in = d_ring[ring_cur].p;
+  da.ring_out = d_ring[ring_cur ^ 1].p;
+  da.avg_frames = avg_frames;
+  da.avg_last = d_avg_last.p;
+  da.checkpoints = d_ckpt.p;
+  da.detect_level = std::min(cfg.start_level, cfg.stop_level);
+  da.entries = d_entries.p;
+  da.entry_count = d_entry_count.p;
+  da.entry_capacity = entry_capacity;
+  da.spec_out = M;
+  da.spec_sum = ss ? ss->sum.p : nullptr;
+  da.spec_slot = d_spec_slot.p;
+  da.spec_div = d_spec_div.p;
+  da.spec_rows = d_spec_rows.p;
+  da.dense_q = want_dense_q ? d_dense_q.p : nullptr;
+  da.dense_avg = want_dense_avg ? d_dense_avg.p : nullptr;
+  da.dense_box = want_dense_box ? d_dense_box.p : nullptr;
+  {
+    const int half = cfg.grouping_x / 2;
+    const int width = kDetectBinsPerCta + 2 * half;
+    const size_t smem = sizeof(float) * 2 * kDetectTileFrames * width;
+    const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+    k_detect<<<grid, kDetectBinsPerCta + 64, smem, stream>>>(da);
+    CU(cudaGetLastError());
+  }
+  // push context for the tracker's device queries
+  cur_frames = T;
+  cur_noise_samples = da.noise_samples;
+  cur_avg_frames_before = avg_frames;
+  thr_host_valid = false;
+  // host mirrors of the scalar state
+  if (!ns->ready) {
+    ns->samples = std::min(ns->samples + T, cfg.learn_frames);
+    ns->ready = ns->samples >= cfg.learn_frames;
+  }
+  avg_frames = std::min(avg_frames + T, Y);
+  ring_cur ^= 1;
+
+  // ---- results: detection entries -> tracker ----
+  int* h_count = h_small.p + max_frames;
+  CU(cudaMemcpyAsync(h_count, d_entry_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  const int n_entries = *h_count;
+  if (n_entries > entry_capacity) return fail(B2S_E_OVERFLOW, "%d detection entries exceed detect_capacity %d", n_entries, entry_capacity);
+  std::vector<DetectEntry> entries(n_entries);
+  std::vector<int> frame_begin(T + 1, 0);
+  if (n_entries > 0) {
+    CU(cudaMemcpyAsync(h_entries.p, d_entries.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n_entries; ++i) frame_begin[h_entries.p[i].frame + 1]++;
+    for (int t = 0; t < T; ++t) frame_begin[t + 1] += frame_begin[t];
+    std::vector<int> cursor(frame_begin.begin(), frame_begin.end() - 1);
+    for (int i = 0; i < n_entries; ++i) entries[cursor[h_entries.p[i].frame]++] = h_entries.p[i];
+    for (int t = 0; t < T; ++t) {
+      std::sort(entries.begin() + frame_begin[t], entries.begin() + frame_begin[t + 1], [](const DetectEntry& x, const DetectEntry& y) { return x.bin < y.bin; });
+    }
+  }
+  const bool every = out && out->frame_tx_count;
+  std::vector<Tracker::FrameState> states;
+  rc = tracker.run(entries, frame_begin, frames, t0_ms, period_ms, frame_offset, *this, every, states);
+  if (rc) return rc;
+
+  // ---- copy-out ----
+  if (out) {
+    out->n_detect_entries += n_entries;
+    out->n_spectrogram_rows += n_slots;
+    if (every) {
+      for (int t = 0; t < T; ++t) out->frame_tx_count[frame_offset + t] = 0;
+      for (const auto& fs : states) {
+        out->frame_tx_count[frame_offset + fs.frame] =
+            tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
+      }
+    }
+    // the mailbox after the last frame of this chunk
+    out->n_transmissions = 0;
+    if (!states.empty() && states.back().frame == T - 1) {
+      const int total = tracker.sorted_transmissions(states.back(), out->transmissions, B2S_MAX_TX);
+      out->n_transmissions = std::min(total, B2S_MAX_TX);
+    }
+    if (out->peak_index) CU(cudaMemcpyAsync(out->peak_index + frame_offset, d_peak_idx.p, sizeof(int) * T, cudaMemcpyDeviceToHost, stream));
+    if (out->peak_value) CU(cudaMemcpyAsync(out->peak_value + frame_offset, d_peak_val.p, sizeof(float) * T, cudaMemcpyDeviceToHost, stream));
+    const size_t row_bytes = sizeof(float) * static_cast<size_t>(T) * n, off = frame_offset * n;
+    if (out->psd_db) CU(cudaMemcpyAsync(out->psd_db + off, d_psd.p, row_bytes, cudaMemcpyDeviceToHost, stream));
+    if (out->noise_sub_db) CU(cudaMemcpyAsync(out->noise_sub_db + off, d_dense_q.p, row_bytes, cudaMemcpyDeviceToHost, stream));
+    if (out->avg_db) CU(cudaMemcpyAsync(out->avg_db + off, d_dense_avg.p, row_bytes, cudaMemcpyDeviceToHost, stream));
+    if (out->box_db) CU(cudaMemcpyAsync(out->box_db + off, d_dense_box.p, row_bytes, cudaMemcpyDeviceToHost, stream));
+  }
+  if (n_slots > 0) {
+    std::vector<int8_t> rows(static_cast<size_t>(n_slots) * M);
+    CU(cudaMemcpyAsync(rows.data(), d_spec_rows.p, rows.size(), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (int s = 0; s < n_slots; ++s) {
+      sent.push_back(SentRow{slot_time[s], center, std::vector<int8_t>(rows.begin() + static_cast<size_t>(s) * M, rows.begin() + static_cast<size_t>(s + 1) * M)});
+    }
+  }
+  CU(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stand-alone device Averager
+// ------------------------------------------------------------------------------------------------------------
+struct b2s_averager {
+  b2s_engine* engine = nullptr;
+  int size = 0, group = 0, frames = 0, cur = 0;
+  DevBuf<float> sum, ring[2], avg, rows;
+  ~b2s_averager() {
+    sum.release();
+    ring[0].release();
+    ring[1].release();
+    avg.release();
+    rows.release();
+  }
+  int reset() {
+    CU(cudaMemset(sum.p, 0, sizeof(float) * size));
+    CU(cudaMemset(ring[0].p, 0, sizeof(float) * size * group));
+    CU(cudaMemset(ring[1].p, 0, sizeof(float) * size * group));
+    std::vector<float> nd(size, kNoData);
+    CU(cudaMemcpy(avg.p, nd.data(), sizeof(float) * size, cudaMemcpyHostToDevice));
+    frames = 0;
+    cur = 0;
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b2s_last_error(void) { return g_error.c_str(); }
+int b2s_version(void) { return B2S_VERSION; }
+
+int b2s_engine_create(int cuda_device, b2s_engine** out) {
+  if (!out) return fail(B2S_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) return fail(B2S_E_CUDA, "no usable CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(err));
+  if (cuda_device < 0 || cuda_device >= count) return fail(B2S_E_INVALID, "cuda_device %d out of range (0..%d)", cuda_device, count - 1);
+  b2s_engine* e = new b2s_engine();
+  e->device = cuda_device;
+  CU(cudaSetDevice(cuda_device));
+  CU(cudaGetDeviceProperties(&e->prop, cuda_device));
+  if (e->prop.major < 10) {
+    const int major = e->prop.major, minor = e->prop.minor;
+    delete e;
+    return fail(B2S_E_CUDA, "device is sm_%d%d; this build targets sm_100a (B200) only", major, minor);
+  }
+  e->sm_count = e->prop.multiProcessorCount;
+  *out = e;
+  return 0;
+}
+int b2s_engine_destroy(b2s_engine* e) {
+  delete e;
+  return 0;
+}
+int b2s_engine_device_name(b2s_engine* e, char* buf, size_t cap) {
+  if (!e || !buf || cap == 0) return fail(B2S_E_INVALID, "bad argument");
+  snprintf(buf, cap, "%s (%d SMs)", e->prop.name, e->sm_count);
+  return 0;
+}
+
+void b2s_default_config(b2s_band_config* cfg, int32_t sample_rate_hz, int32_t center_hz, int32_t recording_bandwidth_hz) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  const int n = host::fft_size_for(sample_rate_hz, 250);  // SIGNAL_DETECTION_MAX_STEP, config.h:33
+  const double step = static_cast<double>(sample_rate_hz) / n;
+  cfg->fft_size = n;
+  cfg->sample_rate_hz = sample_rate_hz;
+  cfg->frame_stride_samples = n * host::decimator_factor(sample_rate_hz, n);
+  cfg->iq_format = B2S_IQ_CS8;
+  cfg->iq_scale = 1.0f / 127.0f;
+  cfg->window_kind = B2S_WINDOW_HAMMING;
+  cfg->grouping_x = 21;
+  cfg->grouping_y = 21;
+  cfg->group_size_bins = static_cast<int32_t>(std::ceil(recording_bandwidth_hz / step));  // sdr_device.cpp:151
+  cfg->start_level = 8.0f;
+  cfg->stop_level = 5.0f;
+  const double period = static_cast<double>(cfg->frame_stride_samples) * 1000.0 / sample_rate_hz;
+  cfg->learn_frames = b2s_learn_frames_from_ms(2000, period);
+  cfg->center_hz = center_hz;
+  cfg->range_lo_hz = center_hz - sample_rate_hz / 2;
+  cfg->range_hi_hz = center_hz + sample_rate_hz / 2;
+  cfg->tuning_step_hz = 2500;
+  cfg->min_time_ms = 2000;
+  cfg->timeout_ms = 2000;
+  cfg->max_time_ms = 600000;
+  cfg->spectrogram_out_size = std::min(n, std::min(16384, host::fft_size_for(sample_rate_hz, 1000)));
+  cfg->spectrogram_interval_ms = 1000;
+}
+
+int b2s_band_create(b2s_engine* e, const b2s_band_config* cfg, b2s_band** out) {
+  if (!e || !cfg || !out) return fail(B2S_E_INVALID, "NULL argument");
+  *out = nullptr;
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  b2s_band* b = new b2s_band();
+  rc = b->init(e, *cfg);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+int b2s_band_destroy(b2s_band* b) {
+  if (b) {
+    cudaSetDevice(b->engine->device);
+    delete b;
+  }
+  return 0;
+}
+int b2s_band_set_stream(b2s_band* b, void* cuda_stream) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  b->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->own_stream;
+  return 0;
+}
+
+int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, double frame_period_ms, b2s_result* out) {
+  if (!b || (!iq && n_frames)) return fail(B2S_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  if (out) {
+    out->n_transmissions = 0;
+    out->n_detect_entries = 0;
+    out->n_spectrogram_rows = 0;
+  }
+  const size_t bytes_per_sample = b->cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
+  const size_t stride_bytes = static_cast<size_t>(b->cfg.frame_stride_samples) * bytes_per_sample;
+  const bool on_device = (b->cfg.flags & B2S_FLAG_IQ_ON_DEVICE) != 0;
+  for (size_t done = 0; done < n_frames;) {
+    const size_t chunk = std::min(n_frames - done, static_cast<size_t>(b->max_frames));
+    const char* src = static_cast<const char*>(iq) + done * stride_bytes;
+    const void* dev = src;
+    if (!on_device) {
+      // last frame only needs N samples, not a whole stride
+      const size_t bytes = (chunk - 1) * stride_bytes + static_cast<size_t>(b->cfg.fft_size) * bytes_per_sample;
+      int rc = b->d_iq.alloc(static_cast<size_t>(b->max_frames) * stride_bytes);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(b->d_iq.p, src, bytes, cudaMemcpyHostToDevice, b->stream));
+      dev = b->d_iq.p;
+    }
+    int rc = b->push_chunk(dev, chunk, t0_ms, frame_period_ms, done, out);
+    if (rc) return rc;
+    done += chunk;
+  }
+  return 0;
+}
+
+int b2s_band_reset(b2s_band* b) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  b->tracker.reset();
+  return b->reset_averager();
+}
+
+int b2s_band_set_center(b2s_band* b, int32_t center_hz, int32_t lo, int32_t hi) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  b->center = center_hz;
+  b->tracker.p.center = center_hz;
+  b->tracker.p.range_lo = lo;
+  b->tracker.p.range_hi = hi;
+  return 0;
+}
+
+int b2s_band_get_averager(b2s_band* b, float* sum, float* avg, float* ring, int32_t* frames) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  const size_t n = b->cfg.fft_size, Y = b->cfg.grouping_y;
+  if (sum) CU(cudaMemcpy(sum, b->d_sum.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  if (avg) CU(cudaMemcpy(avg, b->d_avg_last.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  if (ring) CU(cudaMemcpy(ring, b->d_ring[b->ring_cur].p, sizeof(float) * n * Y, cudaMemcpyDeviceToHost));
+  if (frames) *frames = b->avg_frames;
+  return 0;
+}
+
+int b2s_band_get_noise(b2s_band* b, float* threshold, int32_t* samples, int32_t* ready) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  auto it = b->noise.find(b->center);
+  if (it == b->noise.end()) {
+    if (samples) *samples = 0;
+    if (ready) *ready = 0;
+    if (threshold) {
+      for (int i = 0; i < b->cfg.fft_size; ++i) threshold[i] = -std::numeric_limits<float>::max();
+    }
+    return 0;
+  }
+  if (threshold) CU(cudaMemcpy(threshold, it->second.threshold.p, sizeof(float) * b->cfg.fft_size, cudaMemcpyDeviceToHost));
+  if (samples) *samples = it->second.samples;
+  if (ready) *ready = it->second.ready ? 1 : 0;
+  return 0;
+}
+
+int b2s_band_get_spectrogram(b2s_band* b, int64_t* times, int32_t* centers, int8_t* rows, int cap, int consume, int* count) {
+  if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  const int M = b->cfg.spectrogram_out_size;
+  const int total = static_cast<int>(b->sent.size());
+  for (int i = 0; i < total && i < cap; ++i) {
+    if (times) times[i] = b->sent[i].time;
+    if (centers) centers[i] = b->sent[i].center;
+    if (rows) std::memcpy(rows + static_cast<size_t>(i) * M, b->sent[i].row.data(), M);
+  }
+  *count = total;
+  if (consume) b->sent.clear();
+  return 0;
+}
+
+int b2s_band_get_signals(b2s_band* b, int32_t* keys, int64_t* first, int64_t* last, float* power, int cap, int* count) {
+  if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  int i = 0;
+  for (const auto& kv : b->tracker.signals) {
+    if (i < cap) {
+      if (keys) keys[i] = kv.first;
+      if (first) first[i] = kv.second.first;
+      if (last) last[i] = kv.second.last;
+      if (power) power[i] = kv.second.power;
+    }
+    ++i;
+  }
+  *count = i;
+  return 0;
+}
+
+// ---- stand-alone operators ----
+int b2s_averager_create(b2s_engine* e, int size, int group_size, b2s_averager** out) {
+  if (!e || !out || size < 1 || group_size < 1) return fail(B2S_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  b2s_averager* a = new b2s_averager();
+  a->engine = e;
+  a->size = size;
+  a->group = group_size;
+  int rc = a->sum.alloc(size);
+  if (!rc) rc = a->ring[0].alloc(static_cast<size_t>(size) * group_size);
+  if (!rc) rc = a->ring[1].alloc(static_cast<size_t>(size) * group_size);
+  if (!rc) rc = a->avg.alloc(size);
+  if (!rc) rc = a->reset();
+  if (rc) {
+    delete a;
+    return rc;
+  }
+  *out = a;
+  return 0;
+}
+int b2s_averager_destroy(b2s_averager* a) {
+  delete a;
+  return 0;
+}
+int b2s_averager_push_many(b2s_averager* a, const float* rows, int count) {
+  if (!a || !rows || count < 0) return fail(B2S_E_INVALID, "bad argument");
+  if (count == 0) return 0;
+  CU(cudaSetDevice(a->engine->device));
+  int rc = a->rows.alloc(static_cast<size_t>(count) * a->size);
+  if (rc) return rc;
+  CU(cudaMemcpy(a->rows.p, rows, sizeof(float) * count * a->size, cudaMemcpyHostToDevice));
+  k_averager_push<<<(a->size + 127) / 128, 128>>>(a->rows.p, count, a->size, a->group, a->sum.p, a->ring[a->cur].p, a->ring[a->cur ^ 1].p, a->frames, a->avg.p);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  a->cur ^= 1;
+  a->frames = std::min(a->frames + count, a->group);
+  return 0;
+}
+int b2s_averager_push(b2s_averager* a, const float* data) { return b2s_averager_push_many(a, data, 1); }
+int b2s_averager_reset(b2s_averager* a) {
+  if (!a) return fail(B2S_E_INVALID, "NULL averager");
+  CU(cudaSetDevice(a->engine->device));
+  return a->reset();
+}
+int b2s_averager_average(b2s_averager* a, float* out) {
+  if (!a || !out) return fail(B2S_E_INVALID, "bad argument");
+  CU(cudaMemcpy(out, a->avg.p, sizeof(float) * a->size, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b2s_averager_data(b2s_averager* a, float* out) {
+  if (!a || !out) return fail(B2S_E_INVALID, "bad argument");
+  CU(cudaMemcpy(out, a->ring[a->cur].p, sizeof(float) * a->size * a->group, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b2s_averager_sum(b2s_averager* a, float* out, int32_t* frames) {
+  if (!a) return fail(B2S_E_INVALID, "bad argument");
+  if (out) CU(cudaMemcpy(out, a->sum.p, sizeof(float) * a->size, cudaMemcpyDeviceToHost));
+  if (frames) *frames = a->frames;
+  return 0;
+}
+
+int b2s_average(b2s_engine* e, const float* in, float* out, int size, int group_size, int rows, int exact) {
+  if (!e || !in || !out || size < 1 || group_size < 1 || rows < 1) return fail(B2S_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  DevBuf<float> din, dout;
+  int rc = din.alloc(static_cast<size_t>(size) * rows);
+  if (!rc) rc = dout.alloc(static_cast<size_t>(size) * rows);
+  if (rc) {
+    din.release();
+    dout.release();
+    return rc;
+  }
+  cudaError_t err = cudaMemcpy(din.p, in, sizeof(float) * size * rows, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) {
+    if (exact) {
+      k_boxcar_serial<<<(rows + 31) / 32, 32>>>(din.p, dout.p, size, group_size, rows);
+    } else {
+      dim3 grid((size + 127) / 128, rows);
+      k_boxcar<<<grid, 128>>>(din.p, dout.p, size, group_size, rows);
+    }
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpy(out, dout.p, sizeof(float) * size * rows, cudaMemcpyDeviceToHost);
+  din.release();
+  dout.release();
+  if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_average: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_frames, float* psd_db, float* power_lin) {
+  if (!e || !cfg || !iq || !psd_db || n_frames == 0) return fail(B2S_E_INVALID, "bad argument");
+  b2s_band_config c = *cfg;
+  if (c.learn_frames < 1) c.learn_frames = 1;
+  if (c.grouping_x < 1) c.grouping_x = 1;
+  if (c.grouping_y < 1) c.grouping_y = 1;
+  if (c.tuning_step_hz < 1) c.tuning_step_hz = 1;
+  int rc = validate_config(c);
+  if (rc) return rc;
+  CU(cudaSetDevice(e->device));
+  SpectralTables tables;
+  DevBuf<unsigned char> diq;
+  DevBuf<float> dpsd, dlin;
+  const size_t n = c.fft_size;
+  const size_t bps = c.iq_format == B2S_IQ_CS8 ? 2 : 8;
+  const size_t stride = static_cast<size_t>(c.frame_stride_samples) * bps;
+  const size_t bytes = (n_frames - 1) * stride + n * bps;
+  rc = tables.build(c);
+  if (!rc) rc = diq.alloc(bytes);
+  if (!rc) rc = dpsd.alloc(n_frames * n);
+  if (!rc && power_lin) rc = dlin.alloc(n_frames * n);
+  cudaError_t err = cudaSuccess;
+  if (!rc) err = cudaMemcpy(diq.p, iq, bytes, cudaMemcpyHostToDevice);
+  if (!rc && err == cudaSuccess) {
+    SpectralArgs sa{};
+    sa.iq = diq.p;
+    sa.frame_stride_bytes = static_cast<long long>(stride);
+    sa.n_frames = static_cast<int>(n_frames);
+    sa.wscale = tables.wscale.p;
+    sa.twiddle = tables.twiddle.p;
+    sa.inv_fs = 1.0f / static_cast<float>(c.sample_rate_hz);
+    sa.psd_db = dpsd.p;
+    sa.power_lin = power_lin ? dlin.p : nullptr;
+    rc = launch_spectrum(e, c.fft_size, c.iq_format, sa, nullptr);
+    if (!rc) err = cudaDeviceSynchronize();
+    if (!rc && err == cudaSuccess) err = cudaMemcpy(psd_db, dpsd.p, sizeof(float) * n_frames * n, cudaMemcpyDeviceToHost);
+    if (!rc && err == cudaSuccess && power_lin) err = cudaMemcpy(power_lin, dlin.p, sizeof(float) * n_frames * n, cudaMemcpyDeviceToHost);
+  }
+  tables.release();
+  diq.release();
+  dpsd.release();
+  dlin.release();
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_psd: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+// ---- host helpers ----
+int b2s_get_fft(int32_t sample_rate_hz, int32_t max_step_hz) { return host::fft_size_for(sample_rate_hz, max_step_hz); }
+int32_t b2s_get_tuned_frequency(int32_t f, int32_t step) { return host::tuned_frequency(f, step); }
+int b2s_get_max_index(const float* data, int size, int index, int group_size) { return host::max_index(data, size, index, group_size); }
+int b2s_contains_with_margin(const int* keys, int n_keys, int index, int margin, int* found) {
+  std::map<int, char> m;
+  for (int i = 0; i < n_keys; ++i) m[keys[i]] = 0;
+  return host::key_within_margin(m, index, margin, found) ? 1 : 0;
+}
+int b2s_most_frequent_value(const int* data, int n) {
+  if (!data || n <= 0) return -1;
+  return host::most_frequent(std::vector<int>(data, data + n));
+}
+int b2s_learn_frames_from_ms(int64_t learning_ms, double frame_period_ms) {
+  // Noise::add (noise_learner.cpp:23): learning completes on the first frame k with t_k >= t_0 + learning_ms
+  size_t k = 0;
+  while (host::frame_time(0, frame_period_ms, k) < learning_ms) ++k;
+  return static_cast<int>(k + 1);
+}
+int b2s_decimator_factor(int32_t sample_rate_hz, int32_t fft_size) { return host::decimator_factor(sample_rate_hz, fft_size); }
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// K2/K3 — the time-ordered half of the hot path, one thread per FFT bin marching through the frames of a push:
+//   NoiseLearner (learn max / subtract)        reference sources/radio/blocks/noise_learner.cpp:11-28,36-67
+//   Averager (ring + running sum, bit-exact)   reference sources/radio/averager.cpp:14-25,40-60
+//   average(avg, GROUPING_X) frequency boxcar  reference sources/utils/utils.cpp:31-53
+//   threshold predicate -> detection entries   reference sources/radio/blocks/transmission.cpp:88-96,113-130
+//   Spectrogram decimate + accumulate + send   reference sources/radio/blocks/spectrogram.cpp:45-75
+// The signal-map bookkeeping (transmission.cpp:70-176) consumes the compact detection entries on the host (tracker.h).
+//
+// Arithmetic contract: every float operation that feeds Averager state is the reference's operation in the reference's
+// order (separate sub / add / IEEE division, no FMA contraction) so m_sum, the ring and m_average are bit-identical.
+// The frequency boxcar is evaluated as an independent left-to-right window sum per bin (the reference carries ONE
+// running sum across the whole row, a 16384-long serial float chain); the two differ by rounding only (<= ~1e-5 dB,
+// asserted in tests) — b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
+#pragma once
+#include "b2s_device.cuh"
+
+namespace b2s {
+
+constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
+constexpr int kDetectTileFrames = 16;   // frames marched between two block barriers
+constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
+
+struct DetectEntry {
+  int frame;  // frame index inside the push
+  int bin;
+  float value;  // boxcar-averaged power (dB above learned noise)
+};
+
+struct DetectArgs {
+  // geometry
+  int n;         // N
+  int n_frames;  // T
+  int group_y;   // Averager depth Y
+  int group_x;   // boxcar width X
+  // inputs
+  const float* psd;  // [T][N] raw PSD rows from K1
+  // noise state (per centre frequency)
+  float* threshold;   // [N], updated in place while learning
+  int noise_samples;  // samples learned before this push
+  int learn_frames;   // frames 0.. with noise_samples + t < learn_frames are learning frames
+  // averager state
+  float* avg_sum;         // [N] m_sum, updated in place
+  const float* ring_in;   // [Y][N] ring before the push, oldest -> newest
+  float* ring_out;        // [Y][N] ring after the push (a different buffer)
+  int avg_frames;         // m_frames before the push
+  float* avg_last;        // [N] m_average after the last frame
+  float* checkpoints;     // [ceil(T/64)][N] m_sum before frame 64*c
+  // detection
+  float detect_level;  // min(start, stop)
+  DetectEntry* entries;
+  int* entry_count;
+  int entry_capacity;
+  // spectrogram
+  int spec_out;           // M (0 = off)
+  float* spec_sum;        // [M]
+  const int* spec_slot;   // [T] -1, or the output row to emit after accumulating this frame (host-planned from the clock)
+  const int* spec_div;    // [slots] Container::m_counter at the moment row `slot` is emitted
+  signed char* spec_rows; // [slots][M]
+  // optional dense rows [T][N]
+  float* dense_q;
+  float* dense_avg;
+  float* dense_box;
+};
+
+// noise-subtracted power of in-push frame t for bin j (NoiseLearner output), recomputable anywhere from the PSD rows
+__device__ __forceinline__ float noise_sub(float p, float thr, bool learning) { return learning ? kNoData : __fsub_rn(p, thr); }
+
+// One Averager::push for one bin: subtract the leaving value, add the new one (two separate roundings, in this order),
+// then m_average = m_sum / groupSize (IEEE division) once groupSize frames were seen — averager.cpp:14-25,40-60.
+__device__ __forceinline__ float averager_step(float& sum, float leaving, float entering, int frames_after, int group) {
+  sum = __fsub_rn(sum, leaving);
+  sum = __fadd_rn(sum, entering);
+  return (frames_after >= group) ? __fdiv_rn(sum, static_cast<float>(group)) : kNoData;
+}
+
+// boxcar value for bin j from a row of averaged values stored with `halo` extra bins on each side.
+// a[halo + (i - j0)] holds bin i; bins outside [0, n) are never read.
+__device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half) {
+  const int lo = max(0, j - half), hi = min(n - 1, j + half);
+  float s = a[idx + (lo - j)];
+  for (int i = lo + 1; i <= hi; ++i) s = __fadd_rn(s, a[idx + (i - j)]);
+  return __fdiv_rn(s, static_cast<float>(hi - lo + 1));
+}
+
+// One CTA owns kDetectBinsPerCta bins (+ halo of X/2 bins on each side computed redundantly).
+__global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectArgs a) {
+  extern __shared__ float sm[];
+  const int half = a.group_x / 2;
+  const int width = kDetectBinsPerCta + 2 * half;  // bins handled by this CTA incl. halo
+  float* avg_tile = sm;                              // [kDetectTileFrames][width]
+  float* psd_tile = sm + kDetectTileFrames * width;  // [kDetectTileFrames][width] (spectrogram decimation only)
+
+  const int n = a.n, T = a.n_frames, Y = a.group_y;
+  const int j0 = blockIdx.x * kDetectBinsPerCta;
+  const int tid = threadIdx.x;
+  const int j = j0 - half + tid;  // my bin
+  const bool active = tid < width && j >= 0 && j < n;
+  const bool owner = active && tid >= half && tid < half + kDetectBinsPerCta;
+
+  float thr = active ? a.threshold[j] : 0.0f;
+  float sum = active ? a.avg_sum[j] : 0.0f;
+  float last_avg = kNoData;
+  const int d = a.spec_out > 0 ? n / a.spec_out : 0;
+  const bool spec_owner = owner && d > 0 && (j % d) == 0;
+  float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
+
+  for (int t0 = 0; t0 < T; t0 += kDetectTileFrames) {
+    const int tf = min(kDetectTileFrames, T - t0);
+    // ---- phase 1: march my bin through the tile (noise -> averager) ----
+    if (active) {
+      for (int f = 0; f < tf; ++f) {
+        const int t = t0 + f;
+        const float p = a.psd[static_cast<size_t>(t) * n + j];
+        if (d > 1) psd_tile[f * width + tid] = p;
+        const bool learning = a.noise_samples + t < a.learn_frames;
+        if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
+        const float q = noise_sub(p, thr, learning);
+        // value leaving the ring (frame t - Y): from the PSD rows when it lies inside this push, else from ring_in
+        float old;
+        if (t >= Y) {
+          const float po = a.psd[static_cast<size_t>(t - Y) * n + j];
+          // thr is final for every frame that was not a learning frame (learning frames contributed -100)
+          old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
+        } else {
+          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row
+        }
+        if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
+        const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
+        avg_tile[f * width + tid] = avg;
+        last_avg = avg;
+        if (owner) {
+          if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
+          if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
+          if (d == 1) {
+            spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
+            const int slot = a.spec_slot[t];
+            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+              spec = 0.0f;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: boxcar + threshold for my bin over the tile; decimated spectrogram ----
+    if (owner) {
+      for (int f = 0; f < tf; ++f) {
+        const int t = t0 + f;
+        float box;
+        if (half == 0 && j == n - 1) {
+          box = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38) and keeps its 0.0
+        } else {
+          box = boxcar_at(avg_tile + f * width, tid, j, n, half);
+        }
+        if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + j] = box;
+        if (box >= a.detect_level) {
+          const int slot = atomicAdd(a.entry_count, 1);
+          if (slot < a.entry_capacity) a.entries[slot] = DetectEntry{t, j, box};
+        }
+      }
+    }
+    if (spec_owner && d > 1) {
+      for (int f = 0; f < tf; ++f) {
+        const int t = t0 + f;
+        float s = 0.0f;
+        for (int i = 0; i < d; ++i) s = __fadd_rn(s, psd_tile[f * width + tid + i]);  // spectrogram.cpp:52-56
+        spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));                  // spectrogram.cpp:57
+        const int slot = a.spec_slot[t];
+        if (slot >= 0) {
+          a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+          spec = 0.0f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (owner) {
+    a.threshold[j] = thr;
+    a.avg_sum[j] = sum;
+    a.avg_last[j] = last_avg;
+    // ring after the push, oldest -> newest: row i is in-push frame T - Y + i, or a surviving row of ring_in
+    for (int i = 0; i < Y; ++i) {
+      const int t = T - Y + i;
+      float q;
+      if (t >= 0) {
+        q = noise_sub(a.psd[static_cast<size_t>(t) * n + j], thr, a.noise_samples + t < a.learn_frames);
+      } else {
+        q = a.ring_in[static_cast<size_t>(T + i) * n + j];
+      }
+      a.ring_out[static_cast<size_t>(i) * n + j] = q;
+    }
+  }
+  if (spec_owner) a.spec_sum[j / d] = spec;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// K3 — window query: max / first-argmax of the boxcar row over [bin_lo, bin_hi] for a range of frames of the last push.
+// This is getMaxIndex(avgPower, N, key, groupSize) of Transmission::updateSignals (transmission.cpp:114-117) for the
+// (rare) frames where no bin of the window reached the detection level, so no detection entry carries the value.
+// Each work item replays the Averager for the window's bins from the nearest m_sum checkpoint (same device functions
+// as k_detect => bit-identical values).
+// ------------------------------------------------------------------------------------------------------------
+struct WindowWork {
+  int bin_lo, bin_hi;      // inclusive window, already clipped to [0, N)
+  int frame_lo, frame_hi;  // [frame_lo, frame_hi) inside one checkpoint interval
+  int out_offset;          // results for frame f go to out[out_offset + (f - frame_lo)]
+};
+
+struct WindowArgs {
+  int n, group_y, group_x;
+  const float* psd;
+  const float* threshold;  // final threshold of the push
+  int noise_samples, learn_frames;
+  const float* ring_in;
+  int avg_frames;
+  const float* checkpoints;
+  const WindowWork* work;
+  float* out_value;
+  int* out_index;
+};
+
+__global__ void __launch_bounds__(256) k_window_query(const WindowArgs a) {
+  extern __shared__ float sm[];
+  const WindowWork w = a.work[blockIdx.x];
+  const int n = a.n, Y = a.group_y, half = a.group_x / 2;
+  const int lo = max(0, w.bin_lo - half), hi = min(n - 1, w.bin_hi + half);
+  const int width = hi - lo + 1;
+  float* sum_s = sm;          // [width]
+  float* avg_s = sm + width;  // [width]
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = w.frame_lo / kCheckpointEvery;
+  for (int i = tid; i < width; i += blockDim.x) sum_s[i] = a.checkpoints[static_cast<size_t>(c) * n + lo + i];
+  __syncthreads();
+  for (int t = c * kCheckpointEvery; t < w.frame_hi; ++t) {
+    for (int i = tid; i < width; i += blockDim.x) {
+      const int j = lo + i;
+      const float thr = a.threshold[j];
+      const float q = noise_sub(a.psd[static_cast<size_t>(t) * n + j], thr, a.noise_samples + t < a.learn_frames);
+      float old;
+      if (t >= Y) {
+        old = noise_sub(a.psd[static_cast<size_t>(t - Y) * n + j], thr, a.noise_samples + (t - Y) < a.learn_frames);
+      } else {
+        old = a.ring_in[static_cast<size_t>(t) * n + j];
+      }
+      float s = sum_s[i];
+      avg_s[i] = averager_step(s, old, q, min(a.avg_frames + t + 1, Y), Y);
+      sum_s[i] = s;
+    }
+    __syncthreads();
+    if (t >= w.frame_lo) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int j = w.bin_lo + tid; j <= w.bin_hi; j += blockDim.x) {
+        float box;
+        if (half == 0 && j == n - 1) {
+          box = 0.0f;
+        } else {
+          box = boxcar_at(avg_s, j - lo, j, n, half);
+        }
+        argmax_combine(bv, bi, box, j);
+      }
+      warp_argmax(bv, bi);
+      if (lane == 0) {
+        red_v[warp] = bv;
+        red_i[warp] = bi;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        bv = lane < nw ? red_v[lane] : -INFINITY;
+        bi = lane < nw ? red_i[lane] : 0x7fffffff;
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+          a.out_value[w.out_offset + (t - w.frame_lo)] = bv;
+          a.out_index[w.out_offset + (t - w.frame_lo)] = bi;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stand-alone operators (operator-level parity with tests/test_averager.cpp and tests/test_utils.cpp)
+// ------------------------------------------------------------------------------------------------------------
+// Averager::push for `count` rows: same per-bin step as k_detect. ring_in/ring_out are [group][size], oldest first.
+__global__ void k_averager_push(const float* rows, int count, int size, int group, float* sum, const float* ring_in, float* ring_out, int frames_before,
+                                float* avg_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= size) return;
+  float s = sum[j];
+  float avg = kNoData;
+  for (int t = 0; t < count; ++t) {
+    const float old = (t >= group) ? rows[static_cast<size_t>(t - group) * size + j] : ring_in[static_cast<size_t>(t) * size + j];
+    avg = averager_step(s, old, rows[static_cast<size_t>(t) * size + j], min(frames_before + t + 1, group), group);
+  }
+  sum[j] = s;
+  avg_out[j] = avg;
+  for (int i = 0; i < group; ++i) {
+    const int t = count - group + i;
+    ring_out[static_cast<size_t>(i) * size + j] = (t >= 0) ? rows[static_cast<size_t>(t) * size + j] : ring_in[static_cast<size_t>(count + i) * size + j];
+  }
+}
+
+// average(in, out, size, groupSize), engine form: independent window sums (same boxcar_at as k_detect)
+__global__ void k_boxcar(const float* in, float* out, int size, int group, int rows) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (j >= size || r >= rows) return;
+  const int half = group / 2;
+  const float* row = in + static_cast<size_t>(r) * size;
+  out[static_cast<size_t>(r) * size + j] = (half == 0 && j == size - 1) ? 0.0f : boxcar_at(row, j, j, size, half);
+}
+
+// average(in, out, size, groupSize), reference form (utils.cpp:31-53): one serial running sum per row, bit-exact.
+__global__ void k_boxcar_serial(const float* in, float* out, int size, int group, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* x = in + static_cast<size_t>(r) * size;
+  float* y = out + static_cast<size_t>(r) * size;
+  const int half = group / 2;
+  float running = 0.0f;
+  int terms = 0;
+  if (half == 0 && size > 0) y[size - 1] = 0.0f;
+  for (int pos = -half; pos < size + half - 1; ++pos) {
+    const int leaving = pos - half - 1, entering = pos + half;
+    if (0 <= leaving && leaving < size) {
+      running = __fsub_rn(running, x[leaving]);
+      terms--;
+    }
+    if (0 <= entering && entering < size) {
+      running = __fadd_rn(running, x[entering]);
+      terms++;
+    }
+    if (0 <= pos && pos < size) y[pos] = __fdiv_rn(running, static_cast<float>(terms));
+  }
+}
+
+}  // namespace b2s

@@ -1,0 +1,316 @@
+// K1 — the frame-parallel half of the hot path: int8-IQ unpack -> window -> N-point FFT -> fftshift -> |X|^2/fs -> dB,
+// plus the per-frame first-maximum of the raw PSD row.
+//
+// Replaces, per frame, the reference's Decimator::work (sources/radio/blocks/decimator.h:11-22), the out-of-tree
+// gr::fft::fft_v<gr_complex,true>(N, window::hamming(N), shift=true) (call site sources/radio/sdr_device.cpp:164),
+// PSD::work (sources/radio/blocks/psd.cpp:11-22) and the argmax scan of NoiseLearner::work
+// (sources/radio/blocks/noise_learner.cpp:53-59).
+//
+// Shape: one persistent CTA per SM slot; each CTA walks frames blockIdx.x, +gridDim.x, ...  The int8 frame (2N bytes)
+// is staged into shared memory by ONE bulk async copy (TMA, cp.async.bulk + mbarrier) that is issued as soon as the
+// previous frame's first pass has consumed the buffer, so the copy of frame f+1 overlaps passes 2.. of frame f.
+// The FFT is a Stockham autosort (decimation in time, twiddle-then-butterfly) with radix-16/8/4/2 passes held in
+// registers (32 complex values per thread); passes exchange through one padded complex buffer in shared memory.
+// The last pass leaves thread b holding bins b + m*N/R, so dB rows leave the SM as fully coalesced 128-byte stores.
+#pragma once
+#include "b2s_device.cuh"
+
+namespace b2s {
+
+// ------------------------------------------------------------------------------------------------------------
+// small DFTs in registers (forward transform, exp(-2 pi i k n / R)), natural-order in-place
+// ------------------------------------------------------------------------------------------------------------
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<1> {
+  __device__ __forceinline__ static void run(float2*) {}
+};
+template <>
+struct Dft<2> {
+  __device__ __forceinline__ static void run(float2* v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+template <>
+struct Dft<4> {
+  __device__ __forceinline__ static void run(float2* v) {
+    const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    const float2 t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+  }
+};
+
+// multiply by W_R^j = exp(-2 pi i j / R), j a compile-time constant after unrolling (R in {8, 16})
+template <int R>
+__device__ __forceinline__ float2 mul_w(float2 a, int j) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+  const int j16 = j * (16 / R);  // express as a 16th root
+  switch (j16 & 15) {
+    case 0: return a;
+    case 4: return mul_mi(a);
+    case 8: return make_float2(-a.x, -a.y);
+    case 12: return make_float2(-a.y, a.x);
+    case 2: return make_float2((a.x + a.y) * H, (a.y - a.x) * H);
+    case 6: return make_float2((a.y - a.x) * H, -(a.x + a.y) * H);
+    case 10: return make_float2(-(a.x + a.y) * H, (a.x - a.y) * H);
+    case 14: return make_float2((a.x - a.y) * H, (a.x + a.y) * H);
+    case 1: return cmul(a, make_float2(C1, -S1));
+    case 3: return cmul(a, make_float2(S1, -C1));
+    case 5: return cmul(a, make_float2(-S1, -C1));
+    case 7: return cmul(a, make_float2(-C1, -S1));
+    case 9: return cmul(a, make_float2(-C1, S1));
+    case 11: return cmul(a, make_float2(-S1, C1));
+    case 13: return cmul(a, make_float2(S1, C1));
+    default: return cmul(a, make_float2(C1, S1));  // 15
+  }
+}
+
+// Cooley-Tukey R = 4 * (R/4): n = N2*n1 + n2, k = k1 + 4*k2
+template <int R>
+struct Dft {
+  __device__ __forceinline__ static void run(float2* v) {
+    constexpr int N2 = R / 4;
+    float2 y[N2][4];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) {
+      float2 a[4];
+#pragma unroll
+      for (int n1 = 0; n1 < 4; ++n1) a[n1] = v[N2 * n1 + n2];
+      Dft<4>::run(a);
+#pragma unroll
+      for (int k1 = 0; k1 < 4; ++k1) y[n2][k1] = mul_w<R>(a[k1], n2 * k1);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      float2 b[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) b[n2] = y[n2][k1];
+      Dft<N2>::run(b);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) v[k1 + 4 * k2] = b[k2];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// pass plans
+// ------------------------------------------------------------------------------------------------------------
+template <int N>
+struct FftPlanT;  // radices R0..R3 (1 = unused), elements per thread E
+template <> struct FftPlanT<256>   { static constexpr int R0 = 16, R1 = 16, R2 = 1,  R3 = 1, E = 16; };
+template <> struct FftPlanT<512>   { static constexpr int R0 = 16, R1 = 8,  R2 = 4,  R3 = 1, E = 16; };
+template <> struct FftPlanT<1024>  { static constexpr int R0 = 16, R1 = 16, R2 = 4,  R3 = 1, E = 16; };
+template <> struct FftPlanT<2048>  { static constexpr int R0 = 16, R1 = 16, R2 = 8,  R3 = 1, E = 16; };
+template <> struct FftPlanT<4096>  { static constexpr int R0 = 16, R1 = 16, R2 = 16, R3 = 1, E = 32; };
+template <> struct FftPlanT<8192>  { static constexpr int R0 = 16, R1 = 16, R2 = 8,  R3 = 4, E = 32; };
+template <> struct FftPlanT<16384> { static constexpr int R0 = 16, R1 = 16, R2 = 16, R3 = 4, E = 32; };
+
+// padded index into the exchange buffer: one float2 of padding per 16 keeps both the strided stores of the first
+// pass and the unit-stride loads of every pass on distinct bank pairs
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+template <int N>
+__host__ __device__ constexpr int exchange_elems() { return N + (N >> 4); }
+
+// input modes
+constexpr int kModeCs8Tma = 0;     // int8 IQ staged through shared memory by bulk async copy (16-byte aligned frames)
+constexpr int kModeCs8Direct = 1;  // int8 IQ read straight from global memory (unaligned frames)
+constexpr int kModeCf32 = 2;       // float IQ read straight from global memory
+
+struct SpectralArgs {
+  const void* iq;               // frame k starts at iq + k * frame_stride_bytes
+  long long frame_stride_bytes;
+  int n_frames;
+  const float* wscale;          // [N] window[n] * iq_scale (CS8) or window[n] (CF32)
+  const float2* twiddle;        // [N] exp(-2 pi i j / N)
+  float inv_fs;                 // 1 / (float)sample_rate
+  float* psd_db;                // [n_frames][N] raw PSD rows (fftshifted)
+  float* power_lin;             // optional [n_frames][N] |X|^2 / fs
+  int* peak_index;              // optional [n_frames]
+  float* peak_value;            // optional [n_frames]
+};
+
+template <int N, int R, int P, int E, int T>
+__device__ __forceinline__ void pass_twiddle_butterfly(float2 (&v)[E], const float2* __restrict__ tw, int tid) {
+  constexpr int BPT = E / R;
+#pragma unroll
+  for (int u = 0; u < BPT; ++u) {
+    const int b = tid + u * T;
+    if (P > 1) {
+      const int k = b & (P - 1);
+      constexpr int TS = N / (P * R);
+#pragma unroll
+      for (int m = 1; m < R; ++m) v[u * R + m] = cmul(v[u * R + m], __ldg(&tw[(k * m) * TS]));
+    }
+    Dft<R>::run(&v[u * R]);
+  }
+}
+
+template <int N, int R, int E, int T>
+__device__ __forceinline__ void pass_load(const float2* X, float2 (&v)[E], int tid) {
+  constexpr int NB = N / R, BPT = E / R;
+#pragma unroll
+  for (int u = 0; u < BPT; ++u) {
+    const int b = tid + u * T;
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[u * R + m] = X[pad16(b + m * NB)];
+  }
+}
+
+template <int N, int R, int P, int E, int T>
+__device__ __forceinline__ void pass_store(float2* X, const float2 (&v)[E], int tid) {
+  constexpr int BPT = E / R;
+#pragma unroll
+  for (int u = 0; u < BPT; ++u) {
+    const int b = tid + u * T;
+    const int k = b & (P - 1);
+    const int j = ((b - k) * R) + k;
+#pragma unroll
+    for (int m = 0; m < R; ++m) X[pad16(j + m * P)] = v[u * R + m];
+  }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralArgs a) {
+  using PL = FftPlanT<N>;
+  constexpr int E = PL::E, T = N / E;
+  constexpr int R0 = PL::R0, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3;
+  constexpr int NP = (R3 > 1) ? 4 : (R2 > 1 ? 3 : 2);
+  constexpr int P1 = R0, P2 = R0 * R1, P3 = R0 * R1 * R2;
+  constexpr int RL = (NP == 4) ? R3 : (NP == 3 ? R2 : R1);  // radix of the last pass
+  static_assert(R0 * R1 * R2 * R3 == N, "plan");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* X = reinterpret_cast<float2*>(smem);
+  unsigned char* raw = smem + sizeof(float2) * exchange_elems<N>();  // 2N bytes (TMA mode only)
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const char* base = static_cast<const char*>(a.iq);
+
+  if (MODE == kModeCs8Tma) {
+    if (tid == 0) {
+      mbar_init(&full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0 && static_cast<int>(blockIdx.x) < a.n_frames) {
+      mbar_arrive_expect_tx(&full_bar, 2 * N);
+      bulk_g2s(raw, base + static_cast<long long>(blockIdx.x) * a.frame_stride_bytes, 2 * N, &full_bar);
+    }
+  }
+
+  uint32_t parity = 0;
+  for (int frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+    float2 v[E];
+    // ---------------- pass 0: unpack + window, radix R0, no twiddles (P = 1) ----------------
+    {
+      constexpr int NB = N / R0, BPT = E / R0;
+      if (MODE == kModeCs8Tma) mbar_wait(&full_bar, parity);
+      parity ^= 1;
+#pragma unroll
+      for (int u = 0; u < BPT; ++u) {
+        const int b = tid + u * T;
+#pragma unroll
+        for (int m = 0; m < R0; ++m) {
+          const int n = b + m * NB;
+          const float w = __ldg(&a.wscale[n]);
+          if (MODE == kModeCs8Tma) {
+            const char2 s = reinterpret_cast<const char2*>(raw)[n];
+            v[u * R0 + m] = make_float2(static_cast<float>(s.x) * w, static_cast<float>(s.y) * w);
+          } else if (MODE == kModeCs8Direct) {
+            const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+            v[u * R0 + m] = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+          } else {
+            const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+            v[u * R0 + m] = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+          }
+        }
+      }
+      pass_twiddle_butterfly<N, R0, 1, E, T>(v, a.twiddle, tid);
+      pass_store<N, R0, 1, E, T>(X, v, tid);
+    }
+    __syncthreads();
+    // the staging buffer is consumed: start the copy of this CTA's next frame (overlaps the remaining passes)
+    if (MODE == kModeCs8Tma && tid == 0) {
+      const int next = frame + gridDim.x;
+      if (next < a.n_frames) {
+        mbar_arrive_expect_tx(&full_bar, 2 * N);
+        bulk_g2s(raw, base + static_cast<long long>(next) * a.frame_stride_bytes, 2 * N, &full_bar);
+      }
+    }
+    // ---------------- middle passes ----------------
+    if (NP >= 3) {
+      pass_load<N, R1, E, T>(X, v, tid);
+      __syncthreads();
+      pass_twiddle_butterfly<N, R1, P1, E, T>(v, a.twiddle, tid);
+      pass_store<N, R1, P1, E, T>(X, v, tid);
+      __syncthreads();
+    }
+    if (NP >= 4) {
+      pass_load<N, R2, E, T>(X, v, tid);
+      __syncthreads();
+      pass_twiddle_butterfly<N, R2, P2, E, T>(v, a.twiddle, tid);
+      pass_store<N, R2, P2, E, T>(X, v, tid);
+      __syncthreads();
+    }
+    // ---------------- last pass + epilogue ----------------
+    pass_load<N, RL, E, T>(X, v, tid);
+    constexpr int PL_ = (NP == 4) ? P3 : (NP == 3 ? P2 : P1);
+    pass_twiddle_butterfly<N, RL, PL_, E, T>(v, a.twiddle, tid);
+
+    // thread holds bins k = b + m * (N / RL): |X|^2 / fs -> 10 log10 (psd.cpp:18), written at (k + N/2) mod N
+    float* row = a.psd_db + static_cast<size_t>(frame) * N;
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+    {
+      constexpr int NB = N / RL, BPT = E / RL;
+      constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 * log10(2)
+#pragma unroll
+      for (int u = 0; u < BPT; ++u) {
+        const int b = tid + u * T;
+#pragma unroll
+        for (int m = 0; m < RL; ++m) {
+          const float2 z = v[u * RL + m];
+          const int k = b + m * NB;
+          const int j = (k + N / 2) & (N - 1);
+          const float pw = fmaf(z.x, z.x, z.y * z.y) * a.inv_fs;
+          const float db = kDbPerLog2 * __log2f(pw);
+          row[j] = db;
+          if (a.power_lin) a.power_lin[static_cast<size_t>(frame) * N + j] = pw;
+          argmax_combine(best_v, best_i, db, j);
+        }
+      }
+    }
+    if (a.peak_index) {
+      warp_argmax(best_v, best_i);
+      if (lane == 0) {
+        red_v[warp] = best_v;
+        red_i[warp] = best_i;
+      }
+    }
+    __syncthreads();  // all reads of X are done before the next frame's first pass overwrites it
+    if (a.peak_index && warp == 0) {
+      constexpr int NW = (T + 31) / 32;
+      float bv = lane < NW ? red_v[lane] : -INFINITY;
+      int bi = lane < NW ? red_i[lane] : 0x7fffffff;
+      warp_argmax(bv, bi);
+      if (lane == 0) {
+        a.peak_index[frame] = bi;
+        if (a.peak_value) a.peak_value[frame] = bv;
+      }
+    }
+  }
+}
+
+}  // namespace b2s

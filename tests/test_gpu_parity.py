@@ -1,0 +1,359 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C-ABI (libb2s.so) and is compared with the
+CPU oracle on the same seeded inputs.
+
+Bars (DESIGN.md "Parity criterion"):
+  * raw PSD rows: |dB error| <= 2e-3 dB; linear power bins: floored criterion |p-p_ref| <= 1e-5*max(p_ref, median)
+    pass fraction >= 99.5 %, worst <= 1e-4, L2-relative <= 1e-6 (an fp32 FFT — FFTW3f included — cannot do better
+    against the exact result; the strict per-bin fraction is printed).
+  * Averager state (m_sum, ring, m_average, m_frames): BIT-EXACT when both sides see identical rows.
+  * detection: per-frame FrequencyFlush lists, signal keys and peak indices EQUAL on margin-safe scenes.
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import ROOT, load_b2s
+from test_oracle_chain import scene, synth
+from test_oracle_kats import run_averager_fixture, _run_averager_script, G
+from test_oracle_spectrum import power_parity_stats
+
+b2s = load_b2s()
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------------------
+# K1: unpack + window + FFT + PSD
+# ------------------------------------------------------------------------------------------------------------
+def _noise_tones(n, frames, seed, stride=None):
+    tones = [synth.Tone(1234.1 * n / 16384), synth.Tone(-3000.1 * n / 16384), synth.Tone(77.1 * n / 16384, amplitude=25), synth.Tone(6000.1 * n / 16384, fm_dev_bins=5)]
+    return synth.make_iq_int8(n, frames, tones, seed=seed, stride=stride)
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_psd_rows_match_oracle(engine, n):
+    frames = 6
+    fs = 20_000_000 if n >= 8192 else 2_048_000
+    cfg = b2s.make_config(n, fs)
+    iq = _noise_tones(n, frames, seed=n)
+    psd, lin = engine.psd(cfg, iq, frames, want_linear=True)
+    ref = np.empty_like(psd)
+    ref_lin = np.empty_like(lin)
+    for k in range(frames):
+        ref[k], ref_lin[k] = ol.oracle_psd_frame(cfg, iq[k * 2 * n : (k + 1) * 2 * n], want_linear=True)
+    assert np.max(np.abs(psd - ref)) <= 2e-3
+    st = power_parity_stats(lin, ref_lin)
+    print(f"\nN={n}: floored pass {st['pass_frac']:.5f} worst {st['worst']:.2e} strict pass {st['strict_frac']:.4f} L2rel {st['l2_rel']:.2e}")
+    assert st["pass_frac"] >= 0.995 and st["worst"] <= 1e-4 and st["l2_rel"] <= 1e-6, st
+    assert np.array_equal(np.argmax(psd, axis=1), np.argmax(ref, axis=1))
+
+
+def test_psd_known_answers_on_gpu(engine):
+    n, fs = 4096, 2_048_000
+    cfg = b2s.make_config(n, fs, iq_scale=1.0)
+    w = ol.hamming(n).astype(np.float64)
+    iq = np.zeros((3, 2 * n), np.int8)
+    iq[0, 0] = 100  # impulse -> flat
+    iq[1, 0::2] = 50  # DC -> main lobe at N/2
+    k = np.arange(n)
+    z = 60 * np.exp(2j * np.pi * k / 4)  # +fs/4 -> 3N/4
+    iq[2, 0::2], iq[2, 1::2] = np.rint(z.real), np.rint(z.imag)
+    p = engine.psd(cfg, iq.reshape(-1), 3)
+    assert np.max(np.abs(p[0] - 10 * np.log10((100 * w[0]) ** 2 / fs))) < 1e-3
+    assert int(np.argmax(p[1])) == n // 2 and abs(p[1, n // 2] - 10 * np.log10((50 * w.sum()) ** 2 / fs)) < 1e-3
+    assert int(np.argmax(p[2])) == 3 * n // 4
+
+
+def test_psd_input_variants(engine):
+    """CF32 input, decimated frames (stride r*N) and a stride that defeats the 16-byte TMA path all give the same rows."""
+    n, fs, frames = 2048, 2_048_000, 5
+    iq = _noise_tones(n, frames, seed=3)
+    base = engine.psd(b2s.make_config(n, fs), iq, frames)
+    f32 = (iq.astype(np.float32) * np.float32(1 / 127.0)).astype(np.float32)
+    cf = engine.psd(b2s.make_config(n, fs, iq_format=b2s.IQ_CF32), f32, frames)
+    assert np.max(np.abs(cf - base)) <= 1e-4
+    # decimator: keep the first N samples of every 3N (decimator.h:16-22)
+    wide = np.zeros((frames, 3 * n * 2), np.int8)
+    wide[:, : 2 * n] = iq.reshape(frames, 2 * n)
+    wide[:, 2 * n :] = 77
+    dec = engine.psd(b2s.make_config(n, fs, decimator=3), wide.reshape(-1), frames)
+    assert np.array_equal(dec, base)
+    cfg = b2s.make_config(n, fs)
+    cfg.frame_stride_samples = n + 3  # 2N+6 bytes: not a multiple of 16 -> direct-load kernel
+    odd = np.zeros((frames, (n + 3) * 2), np.int8)
+    odd[:, : 2 * n] = iq.reshape(frames, 2 * n)
+    assert np.array_equal(engine.psd(cfg, odd.reshape(-1), frames), base)
+
+
+def test_parseval_property_at_full_size(engine):
+    """Size-independent property at BASELINE config-2 geometry (N=16384): sum_k |X_k|^2 = N * sum_n |x_n w_n|^2."""
+    n, fs, frames = 16384, 20_000_000, 64
+    cfg = b2s.make_config(n, fs)
+    iq = _noise_tones(n, frames, seed=99)
+    _, lin = engine.psd(cfg, iq, frames, want_linear=True)
+    w = ol.hamming(n).astype(np.float64)
+    x = iq.reshape(frames, n, 2).astype(np.float64) * (1.0 / 127.0)
+    energy = np.sum((x[..., 0] ** 2 + x[..., 1] ** 2) * w**2, axis=1) * n / fs
+    assert np.max(np.abs(lin.astype(np.float64).sum(axis=1) / energy - 1.0)) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Averager / average() operators — the reference's own unit tests, run against device-backed operators
+# ------------------------------------------------------------------------------------------------------------
+def test_device_averager_reference_kats(engine):
+    g = G["averager"]
+    _run_averager_script(b2s.Averager(engine, g["size"], g["group"]))
+    f = G["averager_fixture"]
+    size, group = f["size"], f["group"]
+    run_averager_fixture(b2s.Averager(engine, size, group), size, group, f["simple"])
+    rows = list(f["big"]["prefix"]) + [[i * 11 + j * 7 for j in range(size)] for i in range(*f["big"]["ramp_i"])]
+    run_averager_fixture(b2s.Averager(engine, size, group), size, group, rows)
+
+
+@pytest.mark.parametrize("size,group,batch", [(5, 3, 1), (4096, 21, 1), (4096, 21, 7), (16384, 21, 50), (1000, 4, 3)])
+def test_device_averager_bitwise_vs_oracle(engine, size, group, batch):
+    rng = np.random.default_rng(size + group + batch)
+    dev, cpu = b2s.Averager(engine, size, group), ol.CpuAverager(size, group, "orc")
+    for step in range(6):
+        if step == 4:
+            dev.reset(), cpu.reset()
+        rows = (rng.standard_normal((batch, size)) * 30 - 20).astype(np.float32)
+        dev.push(rows if batch > 1 else rows[0])
+        for r in rows:
+            cpu.push(r)
+        s_d, f_d = dev.sum()
+        s_c, f_c = cpu.sum()
+        assert f_d == f_c and s_d.tobytes() == s_c.tobytes()
+        assert dev.average().tobytes() == cpu.average().tobytes()
+        assert dev.data().tobytes() == cpu.data().tobytes()
+
+
+def test_device_average_operator(engine):
+    g = G["average"]
+    x = np.array(g["input"], np.float32)
+    for exact in (False, True):
+        np.testing.assert_allclose(engine.average(x, g["group"], exact=exact), np.array(g["expect"], np.float32), rtol=4e-7)
+    rng = np.random.default_rng(4)
+    for size, group in [(9, 5), (100, 21), (4096, 21), (16384, 21), (50, 1), (10, 21), (7, 4)]:
+        x = (rng.standard_normal((3, size)) * 20 - 7).astype(np.float32)
+        ref = np.stack([ol.cpu_average(r, group) for r in x])
+        assert engine.average(x, group, exact=True).tobytes() == ref.tobytes()  # serial form: bit-exact
+        fused = engine.average(x, group, exact=False)
+        assert np.max(np.abs(fused - ref)) <= 1e-4  # fused form: rounding-level difference only
+    x = np.full((1, 4096), -100.0, np.float32)
+    assert np.max(np.abs(engine.average(x, 21) - ol.cpu_average(x[0], 21))) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the whole band chain
+# ------------------------------------------------------------------------------------------------------------
+def _tx(frames):
+    return [[(f, fl, k) for f, fl, k, _ in fr] for fr in frames]
+
+
+DENSE = ("psd_db", "noise_sub_db", "avg_db", "box_db")
+
+
+def _run_both(engine, cfg, iq, frames, period, t0=0, splits=None):
+    band = b2s.Band(engine, cfg)
+    ref = ol.OracleChain(cfg).push(iq, frames, t0, period)
+    if splits is None:
+        got = band.push(iq, frames, t0, period, per_frame=True, dense=DENSE)
+        return band, got, ref
+    raise NotImplementedError
+
+
+@pytest.mark.parametrize("n,fs,frames,learn", [(1024, 2_048_000, 400, 40), (4096, 2_048_000, 260, 30), (256, 2_048_000, 300, 30)])
+def test_band_matches_oracle_end_to_end(engine, n, fs, frames, learn):
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    band, got, ref = _run_both(engine, cfg, iq, frames, period, t0=1000)
+    assert np.max(np.abs(got.psd_db - ref.psd_db)) <= 2e-3
+    assert np.array_equal(got.noise_sub_db[:learn], ref.noise_sub_db[:learn])  # -100 rows
+    assert np.max(np.abs(got.noise_sub_db - ref.noise_sub_db)) <= 4e-3
+    assert np.max(np.abs(got.avg_db - ref.avg_db)) <= 4e-3
+    assert np.max(np.abs(got.box_db - ref.box_db)) <= 4e-3
+    assert np.array_equal(got.peak_index[learn:], ref.peak_index[learn:])
+    assert _tx(got.frame_tx) == _tx(ref.frame_tx)
+    assert sum(len(x) for x in ref.frame_tx) > 50
+    for a, b in zip(got.frame_tx, ref.frame_tx):
+        for (_, _, _, pa), (_, _, _, pb) in zip(a, b):
+            assert abs(pa - pb) <= 4e-3
+    # noise threshold and spectrogram against the oracle
+    thr_g, samples_g, ready_g = band.get_noise()
+    o = ol.OracleChain(cfg)
+    o.push(iq, frames, 1000, period, dense=())
+    thr_o, samples_o, ready_o = o.get_noise()
+    assert (samples_g, ready_g) == (samples_o, ready_o) and np.max(np.abs(thr_g - thr_o)) <= 2e-3
+
+
+def test_averager_state_is_bit_exact_on_identical_rows(engine):
+    """Feed the oracle's Averager the GPU's own noise-subtracted rows: m_sum, ring, m_average, m_frames and every
+    per-frame average row must then be bit-identical (operator-level parity inside the fused chain)."""
+    n, fs, frames, learn = 4096, 2_048_000, 130, 20
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    band = b2s.Band(engine, cfg)
+    got = band.push(iq, frames, 0, period, dense=DENSE)
+    thr, _, _ = band.get_noise()
+    q_expect = np.where(np.arange(frames)[:, None] < learn, np.float32(-100), got.psd_db - thr).astype(np.float32)
+    assert got.noise_sub_db.tobytes() == q_expect.tobytes()  # NoiseLearner arithmetic, exact
+    assert np.array_equal(thr, got.psd_db[:learn].max(axis=0))
+    cpu = ol.CpuAverager(n, cfg.grouping_y, "orc")
+    for k in range(frames):
+        cpu.push(got.noise_sub_db[k])
+        assert cpu.average().tobytes() == got.avg_db[k].tobytes(), k
+    s, a, ring, f = band.get_averager()
+    cs, cf = cpu.sum()
+    assert f == cf and s.tobytes() == cs.tobytes() and a.tobytes() == cpu.average().tobytes() and ring.tobytes() == cpu.data().tobytes()
+    # boxcar: serial reference form on the same rows differs from the fused form by rounding only
+    ref_box = np.stack([ol.cpu_average(r, cfg.grouping_x) for r in got.avg_db])
+    assert np.max(np.abs(got.box_db - ref_box)) <= 1e-4
+
+
+def test_chunked_pushes_equal_one_push(engine):
+    """State carried across b2s_band_push calls (ring hand-over, noise, tracker, spectrogram) — pushes of 1..97 frames,
+    some shorter than the Averager depth — must reproduce the single-push result bit for bit."""
+    n, fs, frames, learn = 1024, 1_024_000, 400, 40  # 1 ms per frame: the frame clock is additive at any split point
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    assert period == 1.0
+    cfg.spectrogram_interval_ms = 40
+    one = b2s.Band(engine, cfg)
+    whole = one.push(iq, frames, 500, period, per_frame=True, dense=DENSE)
+    t_w, c_w, rows_w = one.get_spectrogram()
+    many = b2s.Band(engine, cfg)
+    sizes, k, i = [1, 2, 5, 20, 21, 22, 97, 3, 60, 1, 80], 0, 0
+    tx, parts = [], {d: [] for d in DENSE}
+    while k < frames:
+        m = min(sizes[i % len(sizes)], frames - k)
+        i += 1
+        r = many.push(iq[k * 2 * n :], m, 500 + k, period, per_frame=True, dense=DENSE)
+        tx += r.frame_tx
+        for d in DENSE:
+            parts[d].append(getattr(r, d))
+        k += m
+    for d in DENSE:
+        assert np.concatenate(parts[d]).tobytes() == getattr(whole, d).tobytes(), d
+    assert _tx(tx) == _tx(whole.frame_tx) and sum(len(x) for x in tx) > 50
+    for a, b in zip(one.get_averager(), many.get_averager()):
+        assert np.array_equal(a, b)
+    t_m, c_m, rows_m = many.get_spectrogram()
+    assert np.array_equal(t_w, t_m) and np.array_equal(rows_w, rows_m) and len(t_w) >= 3
+
+
+def test_spectrogram_rows_are_exact_on_identical_rows(engine):
+    n, fs, frames = 1024, 2_048_000, 2300
+    cfg = b2s.make_config(n, fs, learn_frames=5, spectrogram_out_size=256)
+    rng = np.random.default_rng(1)
+    iq = rng.integers(-60, 60, frames * n * 2).astype(np.int8)
+    period = synth.frame_period_ms(n, fs)
+    band = b2s.Band(engine, cfg)
+    got = band.push(iq, frames, 0, period, dense=("psd_db",))
+    times, centers, rows = band.get_spectrogram()
+    assert len(times) == 2 and got.n_spectrogram_rows == 2
+    now = np.floor(np.arange(frames) * period + 0.5).astype(np.int64)
+    last, start = 0, 0
+    for t_sent, row in zip(times, rows):
+        k_send = int(np.argmax(now > last + 1000))
+        assert t_sent == now[k_send]
+        acc = np.zeros(256, np.float32)
+        for k in range(start, k_send + 1):
+            s = np.zeros(256, np.float32)
+            for j in range(4):
+                s = (s + got.psd_db[k, j::4]).astype(np.float32)
+            acc = (acc + (s / np.float32(4)).astype(np.float32)).astype(np.float32)
+        assert np.array_equal(row, np.trunc(acc / np.float32(k_send + 1 - start)).astype(np.int8))
+        last, start = now[k_send], k_send + 1
+    # and against the oracle end to end: off-by-one only where the mean sits on an integer boundary
+    o = ol.OracleChain(cfg)
+    o.push(iq, frames, 0, period, dense=())
+    t_o, _, rows_o = o.get_spectrogram()
+    assert np.array_equal(times, t_o) and np.max(np.abs(rows.astype(int) - rows_o.astype(int))) <= 1
+    # d == 1 path
+    cfg1 = b2s.make_config(n, fs, learn_frames=5, spectrogram_out_size=n)
+    b1 = b2s.Band(engine, cfg1)
+    g1 = b1.push(iq, 2100, 0, period, dense=("psd_db",))
+    t1, _, r1 = b1.get_spectrogram()
+    k_send = int(np.argmax(now > 1000))
+    acc = np.zeros(n, np.float32)
+    for k in range(k_send + 1):
+        acc = (acc + g1.psd_db[k]).astype(np.float32)
+    assert len(t1) == 1 and np.array_equal(r1[0], np.trunc(acc / np.float32(k_send + 1)).astype(np.int8))
+
+
+def test_reset_and_retune_semantics(engine):
+    cfg, tones, iq, period = scene(frames=200, learn=40)
+    n = cfg.fft_size
+    band, o = b2s.Band(engine, cfg), ol.OracleChain(cfg)
+    band.push(iq, 150, 0, period)
+    o.push(iq, 150, 0, period, dense=())
+    thr0, _, ready0 = band.get_noise()
+    band.reset(), o.reset()  # Transmission::resetBuffers: signals + averager cleared, noise kept
+    s, a, ring, f = band.get_averager()
+    assert f == 0 and not s.any() and not ring.any() and np.all(a == -100.0)
+    assert len(band.get_signals()[0]) == 0
+    thr1, _, ready1 = band.get_noise()
+    assert ready0 and ready1 and np.array_equal(thr0, thr1)
+    g = band.push(iq[150 * 2 * n :], 50, 1000, period, per_frame=True, dense=("noise_sub_db", "avg_db"))
+    r = o.push(iq[150 * 2 * n :], 50, 1000, period)
+    assert np.all(g.avg_db[: cfg.grouping_y - 1] == -100.0) and not np.any(g.noise_sub_db == -100.0)
+    assert _tx(g.frame_tx) == _tx(r.frame_tx)
+    # another centre frequency learns its own threshold; the first one is kept (noise_learner.cpp:41-42)
+    band.set_center(cfg.center_hz + 2_000_000, cfg.range_lo_hz + 2_000_000, cfg.range_hi_hz + 2_000_000)
+    g2 = band.push(iq, 45, 2000, period, dense=("noise_sub_db",))
+    assert np.all(g2.noise_sub_db[:40] == -100.0) and not np.any(g2.noise_sub_db[40:] == -100.0)
+    band.set_center(cfg.center_hz, cfg.range_lo_hz, cfg.range_hi_hz)
+    g3 = band.push(iq, 3, 3000, period, dense=("noise_sub_db",))
+    assert not np.any(g3.noise_sub_db == -100.0)
+    assert np.array_equal(band.get_noise()[0], thr0)
+
+
+def test_ignored_ranges_and_scan_range(engine):
+    n, fs, frames, learn = 1024, 2_048_000, 300, 40
+    base, tones, iq, period = scene(n, fs, frames, learn)
+    step = fs / n
+    f0 = base.center_hz + int(tones[0].bin_offset * step)
+    cfg = b2s.make_config(n, fs, learn_frames=learn, recording_bandwidth_hz=16 * fs // n, min_time_ms=20, timeout_ms=30,
+                          ignored=[(f0 - 40 * int(step), f0 + 40 * int(step))], range_hz=(base.center_hz - 900_000, base.center_hz + 1_000_000))
+    band = b2s.Band(engine, cfg)
+    got = band.push(iq, frames, 0, period, per_frame=True)
+    ref = ol.OracleChain(cfg).push(iq, frames, 0, period, dense=())
+    assert _tx(got.frame_tx) == _tx(ref.frame_tx) and sum(len(x) for x in ref.frame_tx) > 20
+
+
+def test_full_size_geometry_detects_and_agrees_on_a_sample(engine):
+    """BASELINE config-2 geometry (N=16384, fs=20 MS/s, reference levels/timeouts): 700 frames through the oracle
+    (seconds on CPU) and through the engine; detections, keys and flush flags equal."""
+    n, fs, frames, learn = 16384, 20_000_000, 700, 100
+    cfg = b2s.make_config(n, fs, learn_frames=learn, min_time_ms=100, timeout_ms=120)
+    tones = synth.standard_scene(n, frames, learn)
+    iq = synth.make_iq_int8(n, frames, tones, seed=synth.seed_for(2), quiet_frames=learn)
+    period = synth.frame_period_ms(n, fs)
+    band = b2s.Band(engine, cfg)
+    got = band.push(iq, frames, 0, period, per_frame=True, dense=("psd_db",))
+    ref = ol.OracleChain(cfg).push(iq, frames, 0, period, dense=("psd_db",))
+    assert np.max(np.abs(got.psd_db - ref.psd_db)) <= 2e-3
+    assert _tx(got.frame_tx) == _tx(ref.frame_tx) and sum(len(x) for x in ref.frame_tx) > 200
+    assert np.array_equal(got.peak_index[learn:], ref.peak_index[learn:])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+# ------------------------------------------------------------------------------------------------------------
+def test_invalid_arguments_return_codes_not_crashes(engine):
+    for bad in (dict(fft_size=1000), dict(fft_size=65536), dict(learn_frames=0), dict(tuning_step_hz=0)):
+        kw = dict(fft_size=1024, learn_frames=10, tuning_step_hz=2500)
+        kw.update(bad)
+        cfg = b2s.make_config(kw.pop("fft_size"), 2_048_000, **kw)
+        with pytest.raises(b2s.B2SError) as e:
+            b2s.Band(engine, cfg)
+        assert "b2s error -1" in str(e.value)
+    cfg, tones, iq, period = scene(frames=120, learn=20)
+    small = b2s.BandConfig.from_buffer_copy(cfg)
+    small.detect_capacity = 8
+    band = b2s.Band(engine, small)
+    with pytest.raises(b2s.B2SError) as e:
+        band.push(iq, 120, 0, period)
+    assert "b2s error -4" in str(e.value)  # B2S_E_OVERFLOW, loud — not a silent truncation
