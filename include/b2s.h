@@ -137,6 +137,19 @@ int b2s_band_set_stream(b2s_band* b, void* cuda_stream);
  * with B2S_FLAG_IQ_ON_DEVICE, device memory. Read-only; may be reused as soon as the call returns. */
 int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, double frame_period_ms, b2s_result* out);
 
+/* ---- profiling (bench.py): per-kernel device time measured with CUDA events on the band's stream ---- */
+typedef struct b2s_profile {
+  double spectral_ms;        /* K1 k_spectrum: unpack+window+FFT+PSD */
+  double detect_ms;          /* K2 k_detect: noise/averager/boxcar/threshold/spectrogram */
+  double window_ms;          /* K3 k_window_query (only when the tracker needs sub-threshold window maxima) */
+  double tracker_host_ms;    /* host bookkeeping (wall clock) */
+  int64_t spectral_launches, detect_launches, window_launches;
+  int64_t pushes, frames;
+  int64_t h2d_bytes, d2h_bytes; /* bytes moved by b2s_band_push itself */
+} b2s_profile;
+int b2s_band_set_profiling(b2s_band* b, int enable);
+int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset);
+
 /* ---- side channels ---- */
 int b2s_band_reset(b2s_band* b); /* Transmission::resetBuffers (transmission.cpp:42-55): drop signals, Averager::reset; noise kept */
 int b2s_band_set_center(b2s_band* b, int32_t center_hz, int32_t range_lo_hz, int32_t range_hi_hz); /* retune, sdr_device.cpp:66-77 */

@@ -78,6 +78,22 @@ class Result(C.Structure):
     ]
 
 
+class Profile(C.Structure):
+    _fields_ = [
+        ("spectral_ms", C.c_double),
+        ("detect_ms", C.c_double),
+        ("window_ms", C.c_double),
+        ("tracker_host_ms", C.c_double),
+        ("spectral_launches", C.c_int64),
+        ("detect_launches", C.c_int64),
+        ("window_launches", C.c_int64),
+        ("pushes", C.c_int64),
+        ("frames", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
+    ]
+
+
 def make_config(
     fft_size: int,
     sample_rate_hz: int,
@@ -164,6 +180,8 @@ def lib():
         L.b2s_band_destroy.argtypes = [C.c_void_p]
         L.b2s_band_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_band_reset.argtypes = [C.c_void_p]
+        L.b2s_band_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.b2s_band_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_int]
         L.b2s_band_set_center.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.b2s_band_get_averager.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.b2s_band_get_noise.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -351,6 +369,14 @@ class Band:
         out.n_detect_entries = res.n_detect_entries
         out.n_spectrogram_rows = res.n_spectrogram_rows
         return out
+
+    def set_profiling(self, enable: bool = True):
+        _check(lib().b2s_band_set_profiling(self._h, 1 if enable else 0))
+
+    def get_profile(self, reset: bool = True) -> Profile:
+        p = Profile()
+        _check(lib().b2s_band_get_profile(self._h, C.byref(p), 1 if reset else 0))
+        return p
 
     def reset(self):
         _check(lib().b2s_band_reset(self._h))

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -250,6 +251,11 @@ struct b2s_band : public DeviceQueries {
   int32_t center = 0;
   Tracker tracker;
 
+  // profiling
+  bool profiling = false;
+  b2s_profile prof{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
   // context of the push being processed (for DeviceQueries)
   int cur_frames = 0;
   int cur_noise_samples = 0;
@@ -265,6 +271,9 @@ struct b2s_band : public DeviceQueries {
     d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
     for (auto& kv : noise) kv.second.threshold.release();
     for (auto& kv : spectro) kv.second.sum.release();
+    for (auto& e : ev) {
+      if (e) cudaEventDestroy(e);
+    }
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 
@@ -369,13 +378,30 @@ struct b2s_band : public DeviceQueries {
     a.out_index = d_wq_idx.p;
     const size_t smem = sizeof(float) * 2 * max_width;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_window_query, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaEvent_t w0 = nullptr, w1 = nullptr;
+    if (profiling) {
+      CU(cudaEventCreate(&w0));
+      CU(cudaEventCreate(&w1));
+      CU(cudaEventRecord(w0, stream));
+    }
     k_window_query<<<static_cast<unsigned>(work.size()), 256, smem, stream>>>(a);
     CU(cudaGetLastError());
+    if (profiling) CU(cudaEventRecord(w1, stream));
+    prof.window_launches += 1;
     std::vector<float> v(total);
     std::vector<int> ix(total);
     CU(cudaMemcpyAsync(v.data(), d_wq_val.p, sizeof(float) * total, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(ix.data(), d_wq_idx.p, sizeof(int) * total, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
+    prof.d2h_bytes += (sizeof(float) + sizeof(int)) * total;
+    prof.h2d_bytes += sizeof(WindowWork) * work.size();
+    if (profiling) {
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, w0, w1));
+      prof.window_ms += ms;
+      cudaEventDestroy(w0);
+      cudaEventDestroy(w1);
+    }
     values.resize(w.size());
     indices.resize(w.size());
     for (size_t q = 0; q < w.size(); ++q) {
@@ -477,7 +503,9 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   sa.power_lin = nullptr;
   sa.peak_index = d_peak_idx.p;
   sa.peak_value = d_peak_val.p;
+  if (profiling) CU(cudaEventRecord(ev[0], stream));
   if ((rc = launch_spectrum(engine, n, cfg.iq_format, sa, stream))) return rc;
+  if (profiling) CU(cudaEventRecord(ev[1], stream));
 
   // ---- plan the spectrogram emissions of this chunk from the clock (Spectrogram::send, spectrogram.cpp:62-75) ----
   int n_slots = 0;
@@ -554,8 +582,10 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     const int width = kDetectBinsPerCta + 2 * half;
     const size_t smem = sizeof(float) * 2 * kDetectTileFrames * width;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+    if (profiling) CU(cudaEventRecord(ev[2], stream));
     k_detect<<<grid, kDetectBinsPerCta + 64, smem, stream>>>(da);
     CU(cudaGetLastError());
+    if (profiling) CU(cudaEventRecord(ev[3], stream));
   }
   // push context for the tracker's device queries
   cur_frames = T;
@@ -575,12 +605,26 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   CU(cudaMemcpyAsync(h_count, d_entry_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
   const int n_entries = *h_count;
+  prof.pushes += 1;
+  prof.frames += T;
+  prof.spectral_launches += 1;
+  prof.detect_launches += 1;
+  prof.d2h_bytes += sizeof(int);
+  if (profiling) {
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    prof.spectral_ms += ms;
+    CU(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+    prof.detect_ms += ms;
+  }
+  const auto host_t0 = std::chrono::steady_clock::now();
   if (n_entries > entry_capacity) return fail(B2S_E_OVERFLOW, "%d detection entries exceed detect_capacity %d", n_entries, entry_capacity);
   std::vector<DetectEntry> entries(n_entries);
   std::vector<int> frame_begin(T + 1, 0);
   if (n_entries > 0) {
     CU(cudaMemcpyAsync(h_entries.p, d_entries.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
+    prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
     for (int i = 0; i < n_entries; ++i) frame_begin[h_entries.p[i].frame + 1]++;
     for (int t = 0; t < T; ++t) frame_begin[t + 1] += frame_begin[t];
     std::vector<int> cursor(frame_begin.begin(), frame_begin.end() - 1);
@@ -593,6 +637,7 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   std::vector<Tracker::FrameState> states;
   rc = tracker.run(entries, frame_begin, frames, t0_ms, period_ms, frame_offset, *this, every, states);
   if (rc) return rc;
+  prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 
   // ---- copy-out ----
   if (out) {
@@ -773,12 +818,33 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
       int rc = b->d_iq.alloc(static_cast<size_t>(b->max_frames) * stride_bytes);
       if (rc) return rc;
       CU(cudaMemcpyAsync(b->d_iq.p, src, bytes, cudaMemcpyHostToDevice, b->stream));
+      b->prof.h2d_bytes += bytes;
       dev = b->d_iq.p;
     }
     int rc = b->push_chunk(dev, chunk, t0_ms, frame_period_ms, done, out);
     if (rc) return rc;
     done += chunk;
   }
+  return 0;
+}
+
+int b2s_band_set_profiling(b2s_band* b, int enable) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  if (enable) {
+    for (auto& e : b->ev) {
+      if (!e) CU(cudaEventCreate(&e));
+    }
+  }
+  b->profiling = enable != 0;
+  return 0;
+}
+int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset) {
+  if (!b || !out) return fail(B2S_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  *out = b->prof;
+  if (reset) b->prof = b2s_profile{};
   return 0;
 }
 
