@@ -195,7 +195,7 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def make_band(flags):
-        cfg = b2s.make_config(N_FFT, SAMPLE_RATE, center_hz=150_000_000 + 1_000_000 * rank, learn_frames=LEARN, max_frames_per_push=T, detect_capacity=T * 256, flags=flags)
+        cfg = b2s.make_config(N_FFT, SAMPLE_RATE, center_hz=150_000_000 + 1_000_000 * rank, learn_frames=LEARN, max_frames_per_push=T, flags=flags)
         band = b2s.Band(eng, cfg)
         band.set_stream(stream.cuda_stream)
         band.set_profiling(True)

@@ -82,7 +82,7 @@ typedef struct b2s_band_config {
   int32_t flags;                /* B2S_FLAG_* */
   /* ---- engine-only sizing (ignored by the oracle) ---- */
   int32_t max_frames_per_push;  /* capacity of the per-push device buffers; 0 -> 4096 */
-  int32_t detect_capacity;      /* capacity (entries) of the per-push detection list; 0 -> 64 per frame */
+  int32_t detect_capacity;      /* detection entries kept per FRAME (bins >= min(start,stop)); 0 -> 256 */
 } b2s_band_config;
 
 /* Fill cfg with the reference's defaults for a device with this sample rate, exactly as setupChains sizes the chain

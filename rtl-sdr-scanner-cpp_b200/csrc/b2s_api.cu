@@ -225,7 +225,7 @@ struct b2s_band : public DeviceQueries {
   std::mutex mutex;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int max_frames = 0;
-  int entry_capacity = 0;
+  int slot_capacity = 0;  // detection entries per frame
 
   SpectralTables tables;
   DevBuf<unsigned char> d_iq;
@@ -235,15 +235,15 @@ struct b2s_band : public DeviceQueries {
   DevBuf<float> d_sum, d_ring[2], d_avg_last, d_ckpt;
   int ring_cur = 0;  // d_ring[ring_cur] = current ring; the other one = ring as it was before the last push
   int avg_frames = 0;
-  DevBuf<DetectEntry> d_entries;
-  DevBuf<int> d_entry_count;
+  DevBuf<DetectEntry> d_slots, d_sorted;
+  DevBuf<int> d_slot_count, d_offsets, d_max_count;
   DevBuf<int> d_spec_slot, d_spec_div;
   DevBuf<signed char> d_spec_rows;
   DevBuf<WindowWork> d_work;
   DevBuf<float> d_wq_val;
   DevBuf<int> d_wq_idx;
   PinBuf<DetectEntry> h_entries;
-  PinBuf<int> h_small;
+  PinBuf<int> h_small, h_offsets;
 
   std::map<int32_t, NoiseSlot> noise;
   std::map<int32_t, SpectroSlot> spectro;
@@ -267,7 +267,7 @@ struct b2s_band : public DeviceQueries {
     tables.release();
     d_iq.release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
     d_peak_idx.release(); d_peak_val.release(); d_sum.release(); d_ring[0].release(); d_ring[1].release(); d_avg_last.release();
-    d_ckpt.release(); d_entries.release(); d_entry_count.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
+    d_ckpt.release(); d_slots.release(); d_sorted.release(); d_slot_count.release(); d_offsets.release(); d_max_count.release(); h_offsets.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
     d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
     for (auto& kv : noise) kv.second.threshold.release();
     for (auto& kv : spectro) kv.second.sum.release();
@@ -418,7 +418,7 @@ struct b2s_band : public DeviceQueries {
     cfg = c;
     CU(cudaSetDevice(e->device));
     max_frames = c.max_frames_per_push > 0 ? c.max_frames_per_push : 4096;
-    entry_capacity = c.detect_capacity > 0 ? c.detect_capacity : max_frames * 64;
+    slot_capacity = c.detect_capacity > 0 ? c.detect_capacity : 256;
     center = c.center_hz;
     CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
@@ -434,11 +434,15 @@ struct b2s_band : public DeviceQueries {
     if ((rc = d_ring[1].alloc(Y * n))) return rc;
     if ((rc = d_avg_last.alloc(n))) return rc;
     if ((rc = d_ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
-    if ((rc = d_entries.alloc(entry_capacity))) return rc;
-    if ((rc = d_entry_count.alloc(1))) return rc;
+    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
+    if ((rc = d_sorted.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
+    if ((rc = d_slot_count.alloc(max_frames))) return rc;
+    if ((rc = d_offsets.alloc(max_frames + 1))) return rc;
+    if ((rc = d_max_count.alloc(1))) return rc;
+    if ((rc = h_offsets.alloc(max_frames + 2))) return rc;
     if ((rc = d_spec_slot.alloc(max_frames))) return rc;
     if ((rc = h_small.alloc(max_frames + 64))) return rc;
-    if ((rc = h_entries.alloc(entry_capacity))) return rc;
+    if ((rc = h_entries.alloc(static_cast<size_t>(max_frames) * 64))) return rc;
     rc = reset_averager();
     if (rc) return rc;
     // tracker parameters
@@ -549,7 +553,8 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   // ---- K2: noise / averager / boxcar / detect / spectrogram ----
   NoiseSlot* ns = nullptr;
   if ((rc = noise_slot(&ns))) return rc;
-  CU(cudaMemsetAsync(d_entry_count.p, 0, sizeof(int), stream));
+  CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
+  CU(cudaMemsetAsync(d_max_count.p, 0, sizeof(int), stream));
   DetectArgs da{};
   da.n = n;
   da.n_frames = T;
@@ -566,9 +571,9 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   da.avg_last = d_avg_last.p;
   da.checkpoints = d_ckpt.p;
   da.detect_level = std::min(cfg.start_level, cfg.stop_level);
-  da.entries = d_entries.p;
-  da.entry_count = d_entry_count.p;
-  da.entry_capacity = entry_capacity;
+  da.slots = d_slots.p;
+  da.slot_count = d_slot_count.p;
+  da.slot_capacity = slot_capacity;
   da.spec_out = M;
   da.spec_sum = ss ? ss->sum.p : nullptr;
   da.spec_slot = d_spec_slot.p;
@@ -579,11 +584,22 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   da.dense_box = want_dense_box ? d_dense_box.p : nullptr;
   {
     const int half = cfg.grouping_x / 2;
-    const int width = kDetectBinsPerCta + 2 * half;
-    const size_t smem = sizeof(float) * 2 * kDetectTileFrames * width;
+    const int hp = (half + 3) & ~3;
+    const int width = kDetectBinsPerCta + 2 * hp;
+    const size_t smem = sizeof(float) * (kDetectBuffers + 1) * kDetectTileFrames * width + sizeof(int) * kDetectTileFrames;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+    static bool configured = false;
+    if (!configured) {
+      CU(cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
     if (profiling) CU(cudaEventRecord(ev[2], stream));
-    k_detect<<<grid, kDetectBinsPerCta + 64, smem, stream>>>(da);
+    k_detect<<<grid, kDetectThreads, smem, stream>>>(da);
+    CU(cudaGetLastError());
+    // order the per-frame slot lists by bin into one dense array
+    k_entries_prefix<<<1, 1024, 0, stream>>>(d_slot_count.p, slot_capacity, T, d_offsets.p, d_max_count.p);
+    CU(cudaGetLastError());
+    k_entries_sort<<<(T * 32 + 255) / 256, 256, 0, stream>>>(d_slots.p, d_slot_count.p, slot_capacity, T, d_offsets.p, d_sorted.p);
     CU(cudaGetLastError());
     if (profiling) CU(cudaEventRecord(ev[3], stream));
   }
@@ -601,15 +617,17 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   ring_cur ^= 1;
 
   // ---- results: detection entries -> tracker ----
-  int* h_count = h_small.p + max_frames;
-  CU(cudaMemcpyAsync(h_count, d_entry_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  int* h_off = h_offsets.p;
+  int* h_max = h_small.p + max_frames;
+  CU(cudaMemcpyAsync(h_off, d_offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, stream));
+  CU(cudaMemcpyAsync(h_max, d_max_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
-  const int n_entries = *h_count;
+  const int n_entries = h_off[T];
   prof.pushes += 1;
   prof.frames += T;
   prof.spectral_launches += 1;
-  prof.detect_launches += 1;
-  prof.d2h_bytes += sizeof(int);
+  prof.detect_launches += 3;
+  prof.d2h_bytes += sizeof(int) * (T + 2);
   if (profiling) {
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ev[0], ev[1]));
@@ -618,24 +636,16 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     prof.detect_ms += ms;
   }
   const auto host_t0 = std::chrono::steady_clock::now();
-  if (n_entries > entry_capacity) return fail(B2S_E_OVERFLOW, "%d detection entries exceed detect_capacity %d", n_entries, entry_capacity);
-  std::vector<DetectEntry> entries(n_entries);
-  std::vector<int> frame_begin(T + 1, 0);
+  if (*h_max > slot_capacity) return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries; detect_capacity is %d per frame", *h_max, slot_capacity);
   if (n_entries > 0) {
-    CU(cudaMemcpyAsync(h_entries.p, d_entries.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, stream));
+    if ((rc = h_entries.alloc(n_entries))) return rc;
+    CU(cudaMemcpyAsync(h_entries.p, d_sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
-    for (int i = 0; i < n_entries; ++i) frame_begin[h_entries.p[i].frame + 1]++;
-    for (int t = 0; t < T; ++t) frame_begin[t + 1] += frame_begin[t];
-    std::vector<int> cursor(frame_begin.begin(), frame_begin.end() - 1);
-    for (int i = 0; i < n_entries; ++i) entries[cursor[h_entries.p[i].frame]++] = h_entries.p[i];
-    for (int t = 0; t < T; ++t) {
-      std::sort(entries.begin() + frame_begin[t], entries.begin() + frame_begin[t + 1], [](const DetectEntry& x, const DetectEntry& y) { return x.bin < y.bin; });
-    }
   }
   const bool every = out && out->frame_tx_count;
   std::vector<Tracker::FrameState> states;
-  rc = tracker.run(entries, frame_begin, frames, t0_ms, period_ms, frame_offset, *this, every, states);
+  rc = tracker.run(h_entries.p, h_off, frames, t0_ms, period_ms, frame_offset, *this, every, states);
   if (rc) return rc;
   prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 

@@ -17,11 +17,12 @@
 namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
-constexpr int kDetectTileFrames = 16;   // frames marched between two block barriers
+constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
+constexpr int kDetectThreads = 256;
+constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
 
-struct DetectEntry {
-  int frame;  // frame index inside the push
+struct DetectEntry {  // one bin whose boxcar power reached min(start, stop) in one frame
   int bin;
   float value;  // boxcar-averaged power (dB above learned noise)
 };
@@ -45,11 +46,11 @@ struct DetectArgs {
   int avg_frames;         // m_frames before the push
   float* avg_last;        // [N] m_average after the last frame
   float* checkpoints;     // [ceil(T/64)][N] m_sum before frame 64*c
-  // detection
-  float detect_level;  // min(start, stop)
-  DetectEntry* entries;
-  int* entry_count;
-  int entry_capacity;
+  // detection: per-frame slot lists
+  float detect_level;     // min(start, stop)
+  DetectEntry* slots;     // [T][slot_capacity]
+  int* slot_count;        // [T] (zeroed before launch); may exceed slot_capacity -> overflow, reported by the host
+  int slot_capacity;
   // spectrogram
   int spec_out;           // M (0 = off)
   float* spec_sum;        // [M]
@@ -82,20 +83,50 @@ __device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n
   return __fdiv_rn(s, static_cast<float>(hi - lo + 1));
 }
 
-// One CTA owns kDetectBinsPerCta bins (+ halo of X/2 bins on each side computed redundantly).
-__global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectArgs a) {
-  extern __shared__ float sm[];
+// 16-byte asynchronous global->shared copy (LDGSTS); used to stream PSD tiles ahead of the march
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA owns kDetectBinsPerCta bins plus a halo of X/2 bins (rounded up to 4) on each side, computed redundantly.
+// PSD tiles of kDetectTileFrames rows are streamed into shared memory with cp.async two tiles ahead; one thread per
+// column marches the tile through noise -> Averager (the only serial chain: two dependent FADDs per frame); then all
+// threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
+__global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
+  extern __shared__ __align__(16) float sm[];
   const int half = a.group_x / 2;
-  const int width = kDetectBinsPerCta + 2 * half;  // bins handled by this CTA incl. halo
-  float* avg_tile = sm;                              // [kDetectTileFrames][width]
-  float* psd_tile = sm + kDetectTileFrames * width;  // [kDetectTileFrames][width] (spectrogram decimation only)
+  const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
+  const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA
+  const int tile_elems = kDetectTileFrames * width;
+  float* psd_tiles = sm;                                       // [kDetectBuffers][TF][width]
+  float* avg_tile = sm + kDetectBuffers * tile_elems;          // [TF][width]
+  int* slot_tile = reinterpret_cast<int*>(avg_tile + tile_elems);  // [TF] spectrogram slot of each frame of the tile
 
   const int n = a.n, T = a.n_frames, Y = a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
+  const int col0 = j0 - hp;  // bin of column 0
   const int tid = threadIdx.x;
-  const int j = j0 - half + tid;  // my bin
+  const int j = col0 + tid;  // my column's bin (march role)
   const bool active = tid < width && j >= 0 && j < n;
-  const bool owner = active && tid >= half && tid < half + kDetectBinsPerCta;
+  const bool owner = active && tid >= hp && tid < hp + kDetectBinsPerCta;
+  const int n_tiles = (T + kDetectTileFrames - 1) / kDetectTileFrames;
+  const int chunks_per_row = width / 4;
+
+  auto issue_tile = [&](int tile) {
+    if (tile < n_tiles) {
+      float* dst = psd_tiles + (tile % kDetectBuffers) * tile_elems;
+      const int t_base = tile * kDetectTileFrames;
+      for (int c = tid; c < kDetectTileFrames * chunks_per_row; c += kDetectThreads) {
+        const int f = c / chunks_per_row, x = (c - f * chunks_per_row) * 4;
+        const int t = t_base + f, col = col0 + x;
+        if (t < T && col >= 0 && col + 3 < n) cp_async16(dst + f * width + x, a.psd + static_cast<size_t>(t) * n + col);
+      }
+    }
+    cp_async_commit();
+  };
 
   float thr = active ? a.threshold[j] : 0.0f;
   float sum = active ? a.avg_sum[j] : 0.0f;
@@ -104,25 +135,36 @@ __global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectA
   const bool spec_owner = owner && d > 0 && (j % d) == 0;
   float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
 
-  for (int t0 = 0; t0 < T; t0 += kDetectTileFrames) {
+  issue_tile(0);
+  issue_tile(1);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int t0 = tile * kDetectTileFrames;
     const int tf = min(kDetectTileFrames, T - t0);
-    // ---- phase 1: march my bin through the tile (noise -> averager) ----
+    cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
+    if (tid < kDetectTileFrames) slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
+    __syncthreads();
+    const float* cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
+    const float* prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
+    // ---- phase 1: one thread per column marches the tile (noise -> averager) ----
     if (active) {
       for (int f = 0; f < tf; ++f) {
         const int t = t0 + f;
-        const float p = a.psd[static_cast<size_t>(t) * n + j];
-        if (d > 1) psd_tile[f * width + tid] = p;
+        const float p = cur[f * width + tid];
         const bool learning = a.noise_samples + t < a.learn_frames;
         if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
         const float q = noise_sub(p, thr, learning);
-        // value leaving the ring (frame t - Y): from the PSD rows when it lies inside this push, else from ring_in
+        // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
         float old;
         if (t >= Y) {
-          const float po = a.psd[static_cast<size_t>(t - Y) * n + j];
-          // thr is final for every frame that was not a learning frame (learning frames contributed -100)
+          float po;
+          if (Y <= kDetectTileFrames) {
+            po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
+          } else {
+            po = a.psd[static_cast<size_t>(t - Y) * n + j];
+          }
           old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
         } else {
-          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row
+          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
         }
         if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
         const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
@@ -133,7 +175,7 @@ __global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectA
           if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
           if (d == 1) {
             spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
-            const int slot = a.spec_slot[t];
+            const int slot = slot_tile[f];
             if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
               a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
               spec = 0.0f;
@@ -143,38 +185,40 @@ __global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectA
       }
     }
     __syncthreads();
-    // ---- phase 2: boxcar + threshold for my bin over the tile; decimated spectrogram ----
-    if (owner) {
-      for (int f = 0; f < tf; ++f) {
-        const int t = t0 + f;
-        float box;
-        if (half == 0 && j == n - 1) {
-          box = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38) and keeps its 0.0
-        } else {
-          box = boxcar_at(avg_tile + f * width, tid, j, n, half);
-        }
-        if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + j] = box;
-        if (box >= a.detect_level) {
-          const int slot = atomicAdd(a.entry_count, 1);
-          if (slot < a.entry_capacity) a.entries[slot] = DetectEntry{t, j, box};
-        }
+    // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid, all threads ----
+    for (int idx = tid; idx < tf * kDetectBinsPerCta; idx += kDetectThreads) {
+      const int f = idx / kDetectBinsPerCta, b = idx - f * kDetectBinsPerCta;
+      const int bin = j0 + b;
+      if (bin >= n) continue;
+      const int t = t0 + f;
+      float box;
+      if (half == 0 && bin == n - 1) {
+        box = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38) and keeps its 0.0
+      } else {
+        box = boxcar_at(avg_tile + f * width, hp + b, bin, n, half);
+      }
+      if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box;
+      if (box >= a.detect_level) {
+        const int pos = atomicAdd(a.slot_count + t, 1);
+        if (pos < a.slot_capacity) a.slots[static_cast<size_t>(t) * a.slot_capacity + pos] = DetectEntry{bin, box};
       }
     }
     if (spec_owner && d > 1) {
       for (int f = 0; f < tf; ++f) {
-        const int t = t0 + f;
         float s = 0.0f;
-        for (int i = 0; i < d; ++i) s = __fadd_rn(s, psd_tile[f * width + tid + i]);  // spectrogram.cpp:52-56
-        spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));                  // spectrogram.cpp:57
-        const int slot = a.spec_slot[t];
+        for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + tid + i]);  // spectrogram.cpp:52-56
+        spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));               // spectrogram.cpp:57
+        const int slot = slot_tile[f];
         if (slot >= 0) {
           a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
           spec = 0.0f;
         }
       }
     }
-    __syncthreads();
+    __syncthreads();       // everyone is done with tile-1's buffer (ring look-back) and with avg_tile / slot_tile
+    issue_tile(tile + 2);  // reuses the buffer of tile-1
   }
+  cp_async_wait<0>();
 
   if (owner) {
     a.threshold[j] = thr;
@@ -195,6 +239,48 @@ __global__ void __launch_bounds__(kDetectBinsPerCta + 64) k_detect(const DetectA
   if (spec_owner) a.spec_sum[j / d] = spec;
 }
 
+// Exclusive prefix of min(slot_count[t], capacity) over the T frames (one CTA), then per-frame ordering of the slot
+// lists by bin into one dense array (one warp per frame, rank sort: bins are distinct inside a frame).
+__global__ void __launch_bounds__(1024) k_entries_prefix(const int* slot_count, int capacity, int n_frames, int* offsets /*[T+1]*/, int* max_count) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x;
+  const int per = (n_frames + 1023) / 1024;
+  const int begin = tid * per, end = min(n_frames, begin + per);
+  int local = 0, biggest = 0;
+  for (int t = begin; t < end; ++t) {
+    local += min(slot_count[t], capacity);
+    biggest = max(biggest, slot_count[t]);
+  }
+  part[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int run = part[tid] - local;
+  for (int t = begin; t < end; ++t) {
+    offsets[t] = run;
+    run += min(slot_count[t], capacity);
+  }
+  if (tid == 1023) offsets[n_frames] = part[1023];
+  atomicMax(max_count, biggest);
+}
+
+__global__ void __launch_bounds__(256) k_entries_sort(const DetectEntry* slots, const int* slot_count, int capacity, int n_frames, const int* offsets, DetectEntry* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_frames) return;
+  const int count = min(slot_count[warp], capacity);
+  const DetectEntry* src = slots + static_cast<size_t>(warp) * capacity;
+  DetectEntry* dst = out + offsets[warp];
+  for (int i = lane; i < count; i += 32) {
+    const DetectEntry e = src[i];
+    int rank = 0;
+    for (int k = 0; k < count; ++k) rank += (src[k].bin < e.bin) ? 1 : 0;
+    dst[rank] = e;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // K3 — window query: max / first-argmax of the boxcar row over [bin_lo, bin_hi] for a range of frames of the last push.

@@ -104,7 +104,7 @@ struct Dft {
 // ------------------------------------------------------------------------------------------------------------
 template <int N>
 struct FftPlanT;  // radices R0..R3 (1 = unused), elements per thread E
-template <> struct FftPlanT<256>   { static constexpr int R0 = 16, R1 = 16, R2 = 1,  R3 = 1, E = 16; };
+template <> struct FftPlanT<256>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 4,  R3 = 1, E = 8;  };  // E = 8 keeps a full warp (32 threads)
 template <> struct FftPlanT<512>   { static constexpr int R0 = 16, R1 = 8,  R2 = 4,  R3 = 1, E = 16; };
 template <> struct FftPlanT<1024>  { static constexpr int R0 = 16, R1 = 16, R2 = 4,  R3 = 1, E = 16; };
 template <> struct FftPlanT<2048>  { static constexpr int R0 = 16, R1 = 16, R2 = 8,  R3 = 1, E = 16; };

@@ -85,43 +85,48 @@ class Tracker {
     std::vector<char> power_known;
   };
 
-  // entries: all detection entries of the push sorted by (frame, bin); frame_begin[t]..frame_begin[t+1] index them.
-  // Produces one FrameState per frame that ends with at least one live signal.
-  // Frame t of this chunk is frame (frame_offset + t) of the caller's push and is stamped accordingly.
-  int run(const std::vector<DetectEntry>& entries, const std::vector<int>& frame_begin, size_t n_frames, int64_t t0_ms, double period_ms,
-          size_t frame_offset, DeviceQueries& dev, bool need_every_frame, std::vector<FrameState>& out) {
+  // entries: the detection entries of the chunk ordered by (frame, bin); frame_begin[t]..frame_begin[t+1] index them.
+  // Produces one FrameState per frame that ends with at least one live signal (only the last frame unless
+  // need_every_frame). Frame t of this chunk is frame (frame_offset + t) of the caller's push and is stamped accordingly.
+  int run(const DetectEntry* entries, const int* frame_begin, size_t n_frames, int64_t t0_ms, double period_ms, size_t frame_offset, DeviceQueries& dev,
+          bool need_every_frame, std::vector<FrameState>& out) {
     out.clear();
-    std::vector<int> cand;
+    const int half_g = p.group_size / 2;
     for (size_t t = 0; t < n_frames; ++t) {
       const int e0 = frame_begin[t], e1 = frame_begin[t + 1];
       if (e0 == e1 && signals.empty()) continue;
       const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
       // ---- addSignals ----
-      cand.clear();
-      for (int e = e0; e < e1; ++e) {
+      // A candidate only changes the map when no key lies within the margin; the power ordering of the candidates
+      // (std::sort in the reference) matters only then, so the list is built and ordered lazily.
+      bool any_new = false;
+      for (int e = e0; e < e1 && !any_new; ++e) {
         const DetectEntry& d = entries[e];
-        if (p.start_level <= d.value && in_range(d.bin) && !ignored(d.bin)) cand.push_back(e);
+        if (p.start_level <= d.value && !host::key_within_margin(signals, d.bin, p.group_size) && in_range(d.bin) && !ignored(d.bin)) any_new = true;
       }
-      std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return entries[a].value > entries[b].value; });  // entries are bin-ascending
-      for (int e : cand) {
-        const int idx = entries[e].bin;
-        if (!host::key_within_margin(signals, idx, p.group_size)) {
-          int key = idx;
-          const int rc = best_index(idx, static_cast<int>(t), dev, &key);
-          if (rc != 0) return rc;
-          signals.insert({key, TrackedSignal{now, now, 0.0f}});
+      if (any_new) {
+        cand_.clear();
+        for (int e = e0; e < e1; ++e) {
+          const DetectEntry& d = entries[e];
+          if (p.start_level <= d.value && in_range(d.bin) && !ignored(d.bin)) cand_.push_back(e);
+        }
+        std::stable_sort(cand_.begin(), cand_.end(), [&](int a, int b) { return entries[a].value > entries[b].value; });  // entries are bin-ascending
+        for (int e : cand_) {
+          const int idx = entries[e].bin;
+          if (!host::key_within_margin(signals, idx, p.group_size)) {
+            int key = idx;
+            const int rc = best_index(idx, static_cast<int>(t), dev, &key);
+            if (rc != 0) return rc;
+            signals.insert({key, TrackedSignal{now, now, 0.0f}});
+          }
         }
       }
       if (signals.empty()) continue;
-      // ---- updateSignals: window maximum of the boxcar row around every key ----
-      FrameState fs;
-      fs.frame = static_cast<int>(t);
-      fs.now = now;
-      for (auto& kv : signals) {
-        const int lo = std::max(0, kv.first - p.group_size / 2), hi = std::min(p.n - 1, kv.first + p.group_size / 2);
-        // entries of this frame are bin-sorted: scan the ones inside the window, keep the first maximum
+      // ---- updateSignals: window maximum of the boxcar row around every key, then clearSignals ----
+      for (auto it = signals.begin(); it != signals.end();) {
+        const int lo = std::max(0, it->first - half_g), hi = std::min(p.n - 1, it->first + half_g);
         int a = e0, b = e1;
-        while (a < b) {  // lower_bound on bin
+        while (a < b) {  // first entry of this frame with bin >= lo
           const int m = (a + b) / 2;
           if (entries[m].bin < lo) a = m + 1; else b = m;
         }
@@ -133,39 +138,31 @@ class Tracker {
             found = true;
           }
         }
-        char known = 1;
+        TrackedSignal& s = it->second;
         if (found) {
-          kv.second.power = best;  // Signal::newData: m_power = avgPower
-          if (p.stop_level <= best) kv.second.last = now;
+          s.power = best;  // Signal::newData: m_power = avgPower
+          if (p.stop_level <= best) s.last = now;
         } else {
           // every bin of the window is below min(start, stop): neither level test can pass; only m_power is unknown
-          known = 0;
-          kv.second.power = std::nanf("");
+          s.power = std::nanf("");
         }
-        fs.power_known.push_back(known);
-      }
-      // ---- clearSignals ----
-      size_t pos = 0;
-      for (auto it = signals.begin(); it != signals.end(); ++pos) {
-        const bool timeout = it->second.last + p.timeout <= now;
-        const bool too_long = it->second.first + p.max_time <= now;
-        if (timeout || too_long) {
+        if (s.last + p.timeout <= now || s.first + p.max_time <= now) {
           it = signals.erase(it);
-          fs.power_known[pos] = 2;  // erased: dropped below
         } else {
           ++it;
         }
       }
-      std::vector<char> known;
-      for (char k : fs.power_known) {
-        if (k != 2) known.push_back(k);
+      if (!signals.empty() && (need_every_frame || t + 1 == n_frames)) {
+        out.emplace_back();
+        FrameState& fs = out.back();
+        fs.frame = static_cast<int>(t);
+        fs.now = now;
+        for (const auto& kv : signals) {
+          fs.keys.push_back(kv.first);
+          fs.sig.push_back(kv.second);
+          fs.power_known.push_back(std::isnan(kv.second.power) ? 0 : 1);
+        }
       }
-      fs.power_known.swap(known);
-      for (const auto& kv : signals) {
-        fs.keys.push_back(kv.first);
-        fs.sig.push_back(kv.second);
-      }
-      if (!fs.keys.empty() && (need_every_frame || t + 1 == n_frames)) out.push_back(std::move(fs));
     }
     return resolve_unknown_powers(dev, out);
   }
@@ -264,6 +261,7 @@ class Tracker {
   }
 
   std::vector<float> scratch_;
+  std::vector<int> cand_;
 };
 
 }  // namespace b2s
