@@ -110,23 +110,30 @@ struct b2s_engine {
 // K1 launcher -------------------------------------------------------------------------------------------------
 namespace {
 
-template <int N, int MODE>
-int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+template <int N, int MODE, bool LIN>
+int launch_spectrum_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   using PL = FftPlanT<N>;
   constexpr int T = N / PL::E;
-  const size_t smem = sizeof(float2) * exchange_elems<N>() + (MODE == kModeCs8Tma ? 2 * N : 0);
+  const size_t smem = sizeof(float2) * (exchange_elems<N>() + TwiddleLayout<N>::SMEM) + (MODE == kModeCs8Tma ? 2 * N : 0);
   static bool configured = false;
   static int ctas_per_sm = 1;
   if (!configured) {
-    CU(cudaFuncSetAttribute(k_spectrum<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum<N, MODE>, T, smem));
+    CU(cudaFuncSetAttribute(k_spectrum<N, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum<N, MODE, LIN>, T, smem));
     if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum<%d> does not fit on an SM", N);
     configured = true;
   }
   const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
-  k_spectrum<N, MODE><<<grid, T, smem, stream>>>(a);
+  k_spectrum<N, MODE, LIN><<<grid, T, smem, stream>>>(a);
   CU(cudaGetLastError());
   return 0;
+}
+template <int N, int MODE>
+int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+  if (!a.peak_index || !a.peak_value) return fail(B2S_E_INVALID, "peak buffers are required");
+  // the |X|^2/fs debug rows exist only in the TMA instantiation's debug twin (parity tests); keep the others lean
+  if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
+  return launch_spectrum_v<N, MODE, false>(e, a, stream);
 }
 
 template <int MODE>
@@ -150,6 +157,25 @@ int launch_spectrum(const b2s_engine* e, int n, int iq_format, const SpectralArg
   return launch_spectrum_n<kModeCs8Direct>(e, n, a, stream);
 }
 
+template <int N>
+void plan_radices_t(int* r) {
+  r[0] = FftPlanT<N>::R0;
+  r[1] = FftPlanT<N>::R1;
+  r[2] = FftPlanT<N>::R2;
+  r[3] = FftPlanT<N>::R3;
+}
+void plan_radices(int n, int* r) {
+  switch (n) {
+    case 256: plan_radices_t<256>(r); break;
+    case 512: plan_radices_t<512>(r); break;
+    case 1024: plan_radices_t<1024>(r); break;
+    case 2048: plan_radices_t<2048>(r); break;
+    case 4096: plan_radices_t<4096>(r); break;
+    case 8192: plan_radices_t<8192>(r); break;
+    default: plan_radices_t<16384>(r); break;
+  }
+}
+
 struct SpectralTables {
   DevBuf<float> wscale;
   DevBuf<float2> twiddle;
@@ -161,17 +187,27 @@ struct SpectralTables {
       // unpack scale folded into the window: x*scale*w -> x*(scale*w); differs from the two-step product by < 1 ulp
       for (int i = 0; i < n; ++i) w[i] = w[i] * cfg.iq_scale;
     }
-    std::vector<float2> tw(n);
-    for (int j = 0; j < n; ++j) {
-      const double ang = -2.0 * M_PI * j / n;
-      tw[j] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+    // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)) in the order of TwiddleLayout<N>
+    std::vector<float2> tw;
+    int radix[4] = {0, 0, 0, 0};
+    plan_radices(n, radix);
+    int P = radix[0];
+    for (int pass = 1; pass < 4 && radix[pass] > 1; ++pass) {
+      const int R = radix[pass];
+      for (int m = 1; m < R; ++m) {
+        for (int k = 0; k < P; ++k) {
+          const double ang = -2.0 * M_PI * (static_cast<double>(k) * m) / (static_cast<double>(P) * R);
+          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+        }
+      }
+      P *= R;
     }
     int rc = wscale.alloc(n);
     if (rc) return rc;
-    rc = twiddle.alloc(n);
+    rc = twiddle.alloc(tw.size() + 1);
     if (rc) return rc;
     CU(cudaMemcpy(wscale.p, w.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(twiddle.p, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(twiddle.p, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
     return 0;
   }
   void release() {
@@ -590,11 +626,16 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
     if (profiling) CU(cudaEventRecord(ev[2], stream));
-    k_detect<<<grid, kDetectThreads, smem, stream>>>(da);
+    if (half == 10) {
+      k_detect<10><<<grid, kDetectThreads, smem, stream>>>(da);
+    } else {
+      k_detect<-1><<<grid, kDetectThreads, smem, stream>>>(da);
+    }
     CU(cudaGetLastError());
     // order the per-frame slot lists by bin into one dense array
     k_entries_prefix<<<1, 1024, 0, stream>>>(d_slot_count.p, slot_capacity, T, d_offsets.p, d_max_count.p);
@@ -626,7 +667,7 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   prof.pushes += 1;
   prof.frames += T;
   prof.spectral_launches += 1;
-  prof.detect_launches += 3;
+  prof.detect_launches += 1;  // k_detect (+ the two small list-ordering kernels, timed with it)
   prof.d2h_bytes += sizeof(int) * (T + 2);
   if (profiling) {
     float ms = 0.0f;
@@ -1040,7 +1081,8 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   CU(cudaSetDevice(e->device));
   SpectralTables tables;
   DevBuf<unsigned char> diq;
-  DevBuf<float> dpsd, dlin;
+  DevBuf<float> dpsd, dlin, dpv;
+  DevBuf<int> dpi;
   const size_t n = c.fft_size;
   const size_t bps = c.iq_format == B2S_IQ_CS8 ? 2 : 8;
   const size_t stride = static_cast<size_t>(c.frame_stride_samples) * bps;
@@ -1049,6 +1091,8 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   if (!rc) rc = diq.alloc(bytes);
   if (!rc) rc = dpsd.alloc(n_frames * n);
   if (!rc && power_lin) rc = dlin.alloc(n_frames * n);
+  if (!rc) rc = dpv.alloc(n_frames);
+  if (!rc) rc = dpi.alloc(n_frames);
   cudaError_t err = cudaSuccess;
   if (!rc) err = cudaMemcpy(diq.p, iq, bytes, cudaMemcpyHostToDevice);
   if (!rc && err == cudaSuccess) {
@@ -1061,6 +1105,8 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
     sa.inv_fs = 1.0f / static_cast<float>(c.sample_rate_hz);
     sa.psd_db = dpsd.p;
     sa.power_lin = power_lin ? dlin.p : nullptr;
+    sa.peak_index = dpi.p;
+    sa.peak_value = dpv.p;
     rc = launch_spectrum(e, c.fft_size, c.iq_format, sa, nullptr);
     if (!rc) err = cudaDeviceSynchronize();
     if (!rc && err == cudaSuccess) err = cudaMemcpy(psd_db, dpsd.p, sizeof(float) * n_frames * n, cudaMemcpyDeviceToHost);
@@ -1070,6 +1116,8 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   diq.release();
   dpsd.release();
   dlin.release();
+  dpv.release();
+  dpi.release();
   if (rc) return rc;
   if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_psd: %s", cudaGetErrorString(err));
   return 0;

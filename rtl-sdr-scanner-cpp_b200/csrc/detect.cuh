@@ -95,14 +95,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // PSD tiles of kDetectTileFrames rows are streamed into shared memory with cp.async two tiles ahead; one thread per
 // column marches the tile through noise -> Averager (the only serial chain: two dependent FADDs per frame); then all
 // threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
+template <int HALF_T>  // HALF_T = X/2 known at compile time (10 for the reference's GROUPING_X = 21), or -1 = runtime
 __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int half = a.group_x / 2;
+  const int half = HALF_T >= 0 ? HALF_T : a.group_x / 2;
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
   const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA
   const int tile_elems = kDetectTileFrames * width;
   float* psd_tiles = sm;                                       // [kDetectBuffers][TF][width]
-  float* avg_tile = sm + kDetectBuffers * tile_elems;          // [TF][width]
+  float* __restrict__ avg_tile = sm + kDetectBuffers * tile_elems;  // [TF][width]
   int* slot_tile = reinterpret_cast<int*>(avg_tile + tile_elems);  // [TF] spectrogram slot of each frame of the tile
 
   const int n = a.n, T = a.n_frames, Y = a.group_y;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const int d = a.spec_out > 0 ? n / a.spec_out : 0;
   const bool spec_owner = owner && d > 0 && (j % d) == 0;
   float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
+  const bool ring_in_smem = Y <= kDetectTileFrames;
 
   issue_tile(0);
   issue_tile(1);
@@ -143,64 +145,98 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
     if (tid < kDetectTileFrames) slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
     __syncthreads();
-    const float* cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
-    const float* prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
-    // ---- phase 1: one thread per column marches the tile (noise -> averager) ----
+    const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
+    const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
+    // ---- phase 1: one thread per column marches the tile (noise -> averager). The loop is fully unrolled so the
+    // shared-memory loads of all 32 frames are in flight ahead of the only serial chain (two FADDs per frame). ----
     if (active) {
-      for (int f = 0; f < tf; ++f) {
-        const int t = t0 + f;
-        const float p = cur[f * width + tid];
-        const bool learning = a.noise_samples + t < a.learn_frames;
-        if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
-        const float q = noise_sub(p, thr, learning);
-        // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
-        float old;
-        if (t >= Y) {
-          float po;
-          if (Y <= kDetectTileFrames) {
-            po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
+#pragma unroll
+      for (int f = 0; f < kDetectTileFrames; ++f) {
+        if (f < tf) {
+          const int t = t0 + f;
+          const float p = cur[f * width + tid];
+          const bool learning = a.noise_samples + t < a.learn_frames;
+          if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
+          const float q = noise_sub(p, thr, learning);
+          // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
+          float old;
+          if (t >= Y) {
+            float po;
+            if (ring_in_smem) {
+              po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
+            } else {
+              po = a.psd[static_cast<size_t>(t - Y) * n + j];
+            }
+            old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
           } else {
-            po = a.psd[static_cast<size_t>(t - Y) * n + j];
+            old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
           }
-          old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
-        } else {
-          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
-        }
-        if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
-        const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
-        avg_tile[f * width + tid] = avg;
-        last_avg = avg;
-        if (owner) {
-          if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
-          if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
-          if (d == 1) {
-            spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
-            const int slot = slot_tile[f];
-            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
-              spec = 0.0f;
+          if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
+          const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
+          avg_tile[f * width + tid] = avg;
+          last_avg = avg;
+          if (owner) {
+            if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
+            if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
+            if (d == 1) {
+              spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
+              const int slot = slot_tile[f];
+              if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+                spec = 0.0f;
+              }
             }
           }
         }
       }
     }
     __syncthreads();
-    // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid, all threads ----
-    for (int idx = tid; idx < tf * kDetectBinsPerCta; idx += kDetectThreads) {
-      const int f = idx / kDetectBinsPerCta, b = idx - f * kDetectBinsPerCta;
-      const int bin = j0 + b;
-      if (bin >= n) continue;
+    // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid; one work item = 8 consecutive bins ----
+    constexpr int SEG = 8;
+    for (int item = tid; item < tf * (kDetectBinsPerCta / SEG); item += kDetectThreads) {
+      const int f = item / (kDetectBinsPerCta / SEG), b0 = (item - f * (kDetectBinsPerCta / SEG)) * SEG;
+      const int bin0 = j0 + b0;
+      if (bin0 >= n) continue;
       const int t = t0 + f;
-      float box;
-      if (half == 0 && bin == n - 1) {
-        box = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38) and keeps its 0.0
+      const float* row = avg_tile + f * width;
+      float box[SEG];
+      const bool interior = HALF_T > 0 && bin0 - half >= 0 && bin0 + SEG - 1 + half < n;
+      if (interior) {
+        // same left-to-right window sum as boxcar_at, for 8 bins at once out of one register window
+        constexpr int H = HALF_T > 0 ? HALF_T : 1;
+        float w[SEG + 2 * H];
+#pragma unroll
+        for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];
+#pragma unroll
+        for (int k = 0; k < SEG; ++k) {
+          float s = w[k];
+#pragma unroll
+          for (int i = 1; i <= 2 * H; ++i) s = __fadd_rn(s, w[k + i]);
+          box[k] = __fdiv_rn(s, static_cast<float>(2 * H + 1));
+        }
       } else {
-        box = boxcar_at(avg_tile + f * width, hp + b, bin, n, half);
+#pragma unroll
+        for (int k = 0; k < SEG; ++k) {
+          const int bin = bin0 + k;
+          if (bin >= n) {
+            box[k] = -INFINITY;
+          } else if (half == 0 && bin == n - 1) {
+            box[k] = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38)
+          } else {
+            box[k] = boxcar_at(row, hp + b0 + k, bin, n, half);
+          }
+        }
       }
-      if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box;
-      if (box >= a.detect_level) {
-        const int pos = atomicAdd(a.slot_count + t, 1);
-        if (pos < a.slot_capacity) a.slots[static_cast<size_t>(t) * a.slot_capacity + pos] = DetectEntry{bin, box};
+#pragma unroll
+      for (int k = 0; k < SEG; ++k) {
+        const int bin = bin0 + k;
+        if (bin < n) {
+          if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
+          if (box[k] >= a.detect_level) {
+            const int pos = atomicAdd(a.slot_count + t, 1);
+            if (pos < a.slot_capacity) a.slots[static_cast<size_t>(t) * a.slot_capacity + pos] = DetectEntry{bin, box[k]};
+          }
+        }
       }
     }
     if (spec_owner && d > 1) {

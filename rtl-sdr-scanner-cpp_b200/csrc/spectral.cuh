@@ -119,6 +119,32 @@ __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 template <int N>
 __host__ __device__ constexpr int exchange_elems() { return N + (N >> 4); }
 
+// Twiddles. Pass p (radix R, product of the previous radices P) multiplies input m of butterfly b by
+// W_{P*R}^{k*m}, k = b mod P. Each pass has its own compact table laid out [m-1][k] so that consecutive lanes
+// (consecutive k) read consecutive entries: conflict-free from shared memory, fully coalesced from global memory.
+// Tables of up to kSmemTwiddleMax entries live in shared memory; the (large) table of the last pass stays in global
+// memory / L2 (3 coalesced loads per radix-4 butterfly).
+constexpr int kSmemTwiddleMax = 4096;
+template <int R, int P>
+__host__ __device__ constexpr int twiddle_entries() { return P > 1 ? (R - 1) * P : 0; }
+template <int R, int P>
+__host__ __device__ constexpr bool twiddle_in_smem() { return P > 1 && (R - 1) * P <= kSmemTwiddleMax; }
+
+template <int N>
+struct TwiddleLayout {
+  using PL = FftPlanT<N>;
+  static constexpr int P1 = PL::R0, P2 = PL::R0 * PL::R1, P3 = PL::R0 * PL::R1 * PL::R2;
+  static constexpr int E1 = twiddle_entries<PL::R1, P1>();
+  static constexpr int E2 = PL::R2 > 1 ? twiddle_entries<PL::R2, P2>() : 0;
+  static constexpr int E3 = PL::R3 > 1 ? twiddle_entries<PL::R3, P3>() : 0;
+  static constexpr int O1 = 0, O2 = E1, O3 = E1 + E2, TOTAL = E1 + E2 + E3;  // offsets into the global table
+  static constexpr bool S1 = twiddle_in_smem<PL::R1, P1>();
+  static constexpr bool S2 = PL::R2 > 1 && twiddle_in_smem<PL::R2, P2>();
+  static constexpr bool S3 = PL::R3 > 1 && twiddle_in_smem<PL::R3, P3>();
+  static constexpr int SO1 = 0, SO2 = S1 ? E1 : 0, SO3 = SO2 + (S2 ? E2 : 0);  // offsets into the shared copy
+  static constexpr int SMEM = SO3 + (S3 ? E3 : 0);
+};
+
 // input modes
 constexpr int kModeCs8Tma = 0;     // int8 IQ staged through shared memory by bulk async copy (16-byte aligned frames)
 constexpr int kModeCs8Direct = 1;  // int8 IQ read straight from global memory (unaligned frames)
@@ -129,25 +155,24 @@ struct SpectralArgs {
   long long frame_stride_bytes;
   int n_frames;
   const float* wscale;          // [N] window[n] * iq_scale (CS8) or window[n] (CF32)
-  const float2* twiddle;        // [N] exp(-2 pi i j / N)
+  const float2* twiddle;        // per-pass compact tables, TwiddleLayout<N>
   float inv_fs;                 // 1 / (float)sample_rate
   float* psd_db;                // [n_frames][N] raw PSD rows (fftshifted)
-  float* power_lin;             // optional [n_frames][N] |X|^2 / fs
-  int* peak_index;              // optional [n_frames]
-  float* peak_value;            // optional [n_frames]
+  float* power_lin;             // optional [n_frames][N] |X|^2 / fs (only read by the DEBUG instantiation)
+  int* peak_index;              // [n_frames]
+  float* peak_value;            // [n_frames]
 };
 
+// tw points at this pass's [m-1][k] table (shared or global)
 template <int N, int R, int P, int E, int T>
 __device__ __forceinline__ void pass_twiddle_butterfly(float2 (&v)[E], const float2* __restrict__ tw, int tid) {
   constexpr int BPT = E / R;
 #pragma unroll
   for (int u = 0; u < BPT; ++u) {
-    const int b = tid + u * T;
     if (P > 1) {
-      const int k = b & (P - 1);
-      constexpr int TS = N / (P * R);
+      const int k = (tid + u * T) & (P - 1);
 #pragma unroll
-      for (int m = 1; m < R; ++m) v[u * R + m] = cmul(v[u * R + m], __ldg(&tw[(k * m) * TS]));
+      for (int m = 1; m < R; ++m) v[u * R + m] = cmul(v[u * R + m], tw[(m - 1) * P + k]);
     }
     Dft<R>::run(&v[u * R]);
   }
@@ -156,11 +181,12 @@ __device__ __forceinline__ void pass_twiddle_butterfly(float2 (&v)[E], const flo
 template <int N, int R, int E, int T>
 __device__ __forceinline__ void pass_load(const float2* X, float2 (&v)[E], int tid) {
   constexpr int NB = N / R, BPT = E / R;
+  static_assert(NB % 16 == 0 && T % 16 == 0, "padding arithmetic below assumes multiples of 16");
+  const int base = pad16(tid);
 #pragma unroll
   for (int u = 0; u < BPT; ++u) {
-    const int b = tid + u * T;
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[u * R + m] = X[pad16(b + m * NB)];
+    for (int m = 0; m < R; ++m) v[u * R + m] = X[base + (u * T + m * NB) + ((u * T + m * NB) >> 4)];  // == pad16(tid + u*T + m*NB)
   }
 }
 
@@ -170,16 +196,36 @@ __device__ __forceinline__ void pass_store(float2* X, const float2 (&v)[E], int 
 #pragma unroll
   for (int u = 0; u < BPT; ++u) {
     const int b = tid + u * T;
-    const int k = b & (P - 1);
-    const int j = ((b - k) * R) + k;
+    if (P == 1) {
+      // j = 16 b + m (R == 16 in every plan's first pass, else R*b): pad16(R*b + m)
+      const int j = b * R;
 #pragma unroll
-    for (int m = 0; m < R; ++m) X[pad16(j + m * P)] = v[u * R + m];
+      for (int m = 0; m < R; ++m) X[pad16(j + m)] = v[u * R + m];
+    } else {
+      const int k = b & (P - 1);
+      const int j = ((b - k) * R) + k;
+      const int pj = pad16(j);
+      if (P % 16 == 0) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) X[pj + m * P + ((m * P) >> 4)] = v[u * R + m];  // == pad16(j + m*P): m*P is a multiple of 16
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) X[pad16(j + m * P)] = v[u * R + m];
+      }
+    }
   }
 }
 
-template <int N, int MODE>
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int N, int MODE, bool DEBUG_LIN>
 __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralArgs a) {
   using PL = FftPlanT<N>;
+  using TL = TwiddleLayout<N>;
   constexpr int E = PL::E, T = N / E;
   constexpr int R0 = PL::R0, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3;
   constexpr int NP = (R3 > 1) ? 4 : (R2 > 1 ? 3 : 2);
@@ -189,7 +235,8 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
 
   extern __shared__ __align__(128) unsigned char smem[];
   float2* X = reinterpret_cast<float2*>(smem);
-  unsigned char* raw = smem + sizeof(float2) * exchange_elems<N>();  // 2N bytes (TMA mode only)
+  float2* tws = X + exchange_elems<N>();                                   // shared copy of the small twiddle tables
+  unsigned char* raw = reinterpret_cast<unsigned char*>(tws + TL::SMEM);  // 2N bytes (TMA mode only), 16-byte aligned
   __shared__ __align__(8) uint64_t full_bar;
   __shared__ float red_v[32];
   __shared__ int red_i[32];
@@ -203,7 +250,22 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
       mbar_init(&full_bar, 1);
       fence_barrier_init();
     }
-    __syncthreads();
+  }
+  // stage the small twiddle tables once per CTA
+  if (TL::S1) {
+    for (int i = tid; i < TL::E1; i += T) tws[TL::SO1 + i] = a.twiddle[TL::O1 + i];
+  }
+  if (TL::S2) {
+    for (int i = tid; i < TL::E2; i += T) tws[TL::SO2 + i] = a.twiddle[TL::O2 + i];
+  }
+  if (TL::S3) {
+    for (int i = tid; i < TL::E3; i += T) tws[TL::SO3 + i] = a.twiddle[TL::O3 + i];
+  }
+  __syncthreads();
+  const float2* tw1 = TL::S1 ? tws + TL::SO1 : a.twiddle + TL::O1;
+  const float2* tw2 = TL::S2 ? tws + TL::SO2 : a.twiddle + TL::O2;
+  const float2* tw3 = TL::S3 ? tws + TL::SO3 : a.twiddle + TL::O3;
+  if (MODE == kModeCs8Tma) {
     if (tid == 0 && static_cast<int>(blockIdx.x) < a.n_frames) {
       mbar_arrive_expect_tx(&full_bar, 2 * N);
       bulk_g2s(raw, base + static_cast<long long>(blockIdx.x) * a.frame_stride_bytes, 2 * N, &full_bar);
@@ -237,7 +299,7 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
           }
         }
       }
-      pass_twiddle_butterfly<N, R0, 1, E, T>(v, a.twiddle, tid);
+      pass_twiddle_butterfly<N, R0, 1, E, T>(v, nullptr, tid);
       pass_store<N, R0, 1, E, T>(X, v, tid);
     }
     __syncthreads();
@@ -253,26 +315,25 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
     if (NP >= 3) {
       pass_load<N, R1, E, T>(X, v, tid);
       __syncthreads();
-      pass_twiddle_butterfly<N, R1, P1, E, T>(v, a.twiddle, tid);
+      pass_twiddle_butterfly<N, R1, P1, E, T>(v, tw1, tid);
       pass_store<N, R1, P1, E, T>(X, v, tid);
       __syncthreads();
     }
     if (NP >= 4) {
       pass_load<N, R2, E, T>(X, v, tid);
       __syncthreads();
-      pass_twiddle_butterfly<N, R2, P2, E, T>(v, a.twiddle, tid);
+      pass_twiddle_butterfly<N, R2, P2, E, T>(v, tw2, tid);
       pass_store<N, R2, P2, E, T>(X, v, tid);
       __syncthreads();
     }
     // ---------------- last pass + epilogue ----------------
     pass_load<N, RL, E, T>(X, v, tid);
     constexpr int PL_ = (NP == 4) ? P3 : (NP == 3 ? P2 : P1);
-    pass_twiddle_butterfly<N, RL, PL_, E, T>(v, a.twiddle, tid);
+    pass_twiddle_butterfly<N, RL, PL_, E, T>(v, NP == 4 ? tw3 : (NP == 3 ? tw2 : tw1), tid);
 
     // thread holds bins k = b + m * (N / RL): |X|^2 / fs -> 10 log10 (psd.cpp:18), written at (k + N/2) mod N
     float* row = a.psd_db + static_cast<size_t>(frame) * N;
     float best_v = -INFINITY;
-    int best_i = 0x7fffffff;
     {
       constexpr int NB = N / RL, BPT = E / RL;
       constexpr float kDbPerLog2 = 3.0102999566398120f;  // 10 * log10(2)
@@ -282,32 +343,42 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
 #pragma unroll
         for (int m = 0; m < RL; ++m) {
           const float2 z = v[u * RL + m];
-          const int k = b + m * NB;
-          const int j = (k + N / 2) & (N - 1);
+          const int j = (b + m * NB + N / 2) & (N - 1);
           const float pw = fmaf(z.x, z.x, z.y * z.y) * a.inv_fs;
-          const float db = kDbPerLog2 * __log2f(pw);
+          const float db = kDbPerLog2 * fast_log2(pw);
           row[j] = db;
-          if (a.power_lin) a.power_lin[static_cast<size_t>(frame) * N + j] = pw;
-          argmax_combine(best_v, best_i, db, j);
+          if (DEBUG_LIN) a.power_lin[static_cast<size_t>(frame) * N + j] = pw;
+          v[u * RL + m].x = db;  // keep for the argmax resolution below
+          best_v = fmaxf(best_v, db);
         }
       }
     }
-    if (a.peak_index) {
-      warp_argmax(best_v, best_i);
-      if (lane == 0) {
-        red_v[warp] = best_v;
-        red_i[warp] = best_i;
-      }
-    }
-    __syncthreads();  // all reads of X are done before the next frame's first pass overwrites it
-    if (a.peak_index && warp == 0) {
+    // first maximum of the row (noise_learner.cpp:53-59): reduce the VALUE, then the lowest index that attains it
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best_v = fmaxf(best_v, __shfl_xor_sync(0xffffffffu, best_v, o));
+    if (lane == 0) red_v[warp] = best_v;
+    __syncthreads();  // also: all reads of X are done before the next frame's first pass overwrites it
+    {
       constexpr int NW = (T + 31) / 32;
-      float bv = lane < NW ? red_v[lane] : -INFINITY;
-      int bi = lane < NW ? red_i[lane] : 0x7fffffff;
-      warp_argmax(bv, bi);
-      if (lane == 0) {
-        a.peak_index[frame] = bi;
-        if (a.peak_value) a.peak_value[frame] = bv;
+      float row_max = red_v[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) row_max = fmaxf(row_max, red_v[w]);
+      int best_i = 0x7fffffff;
+      constexpr int NB = N / RL, BPT = E / RL;
+#pragma unroll
+      for (int u = 0; u < BPT; ++u) {
+#pragma unroll
+        for (int m = 0; m < RL; ++m) {
+          if (v[u * RL + m].x == row_max) best_i = min(best_i, (tid + u * T + m * NB + N / 2) & (N - 1));
+        }
+      }
+      if (tid == 0) red_i[0] = 0x7fffffff;
+      __syncthreads();
+      if (best_i != 0x7fffffff) atomicMin(&red_i[0], best_i);
+      __syncthreads();
+      if (tid == 0) {
+        a.peak_index[frame] = red_i[0];
+        a.peak_value[frame] = row_max;
       }
     }
   }
