@@ -626,15 +626,15 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      CU(cudaFuncSetAttribute(k_detect<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
     if (profiling) CU(cudaEventRecord(ev[2], stream));
-    if (half == 10) {
-      k_detect<10><<<grid, kDetectThreads, smem, stream>>>(da);
+    if (half == 10 && Y == 21) {
+      k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da);
     } else {
-      k_detect<-1><<<grid, kDetectThreads, smem, stream>>>(da);
+      k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da);
     }
     CU(cudaGetLastError());
     // order the per-frame slot lists by bin into one dense array

@@ -74,6 +74,24 @@ __device__ __forceinline__ float averager_step(float& sum, float leaving, float 
   return (frames_after >= group) ? __fdiv_rn(sum, static_cast<float>(group)) : kNoData;
 }
 
+// x / D for a small integer constant D, bit-identical to IEEE division: Markstein's sequence q = x*r, e = fma(-q, D, x),
+// q' = fma(e, r, q) with r = RN(1/D). Verified exhaustively against x / D for every float with |x| in [2^-60, 2^60] and
+// for +0 (D = 1..21); anything outside that range takes the IEEE path. Three FMA-pipe instructions
+// instead of the ~10 instruction + subroutine-call sequence the compiler emits for a correctly rounded division.
+template <int D>
+__device__ __forceinline__ float div_const(float x) {
+  constexpr float d = static_cast<float>(D);
+  constexpr float r = 1.0f / d;
+  const uint32_t bits = __float_as_uint(x);
+  const uint32_t ex = (bits >> 23) & 0xffu;
+  if ((ex - 67u) <= 120u || bits == 0u) {
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, d, x);
+    return __fmaf_rn(e, r, q);
+  }
+  return __fdiv_rn(x, d);
+}
+
 // boxcar value for bin j from a row of averaged values stored with `halo` extra bins on each side.
 // a[halo + (i - j0)] holds bin i; bins outside [0, n) are never read.
 __device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half) {
@@ -95,18 +113,22 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // PSD tiles of kDetectTileFrames rows are streamed into shared memory with cp.async two tiles ahead; one thread per
 // column marches the tile through noise -> Averager (the only serial chain: two dependent FADDs per frame); then all
 // threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
-template <int HALF_T>  // HALF_T = X/2 known at compile time (10 for the reference's GROUPING_X = 21), or -1 = runtime
+// Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
+// or 0 / -1 for the generic runtime-parameter instantiation. The specialised instantiation runs steady-state tiles
+// (no learning frame in the tile or its look-back, t0 >= Y, full tile, no dense debug rows) through a branch-free,
+// fully unrolled fast path; every other tile takes the generic path. Both paths execute the same float operations.
+template <int Y_T, int HALF_T>
 __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int half = HALF_T >= 0 ? HALF_T : a.group_x / 2;
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
   const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA
   const int tile_elems = kDetectTileFrames * width;
-  float* psd_tiles = sm;                                       // [kDetectBuffers][TF][width]
+  float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width]
   float* __restrict__ avg_tile = sm + kDetectBuffers * tile_elems;  // [TF][width]
-  int* slot_tile = reinterpret_cast<int*>(avg_tile + tile_elems);  // [TF] spectrogram slot of each frame of the tile
+  int* slot_tile = reinterpret_cast<int*>(avg_tile + tile_elems);   // [TF] spectrogram slot of each frame of the tile
 
-  const int n = a.n, T = a.n_frames, Y = a.group_y;
+  const int n = a.n, T = a.n_frames, Y = Y_T > 0 ? Y_T : a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
   const int col0 = j0 - hp;  // bin of column 0
   const int tid = threadIdx.x;
@@ -115,6 +137,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const bool owner = active && tid >= hp && tid < hp + kDetectBinsPerCta;
   const int n_tiles = (T + kDetectTileFrames - 1) / kDetectTileFrames;
   const int chunks_per_row = width / 4;
+  const bool dense = a.dense_q || a.dense_avg || a.dense_box;
 
   auto issue_tile = [&](int tile) {
     if (tile < n_tiles) {
@@ -147,12 +170,37 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     __syncthreads();
     const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
     const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
-    // ---- phase 1: one thread per column marches the tile (noise -> averager). The loop is fully unrolled so the
-    // shared-memory loads of all 32 frames are in flight ahead of the only serial chain (two FADDs per frame). ----
+    // steady state: whole tile, ring look-back inside the push, no learning frame in the tile or in its look-back
+    const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= Y && (a.noise_samples + t0 - Y >= a.learn_frames) && !dense;
+
+    // ---- phase 1: one thread per column marches the tile (noise -> averager) ----
     if (active) {
+      if (steady) {
+        if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
+        constexpr int YC = Y_T > 0 ? Y_T : 1;
+        const bool spec_on = (d == 1) && owner;
 #pragma unroll
-      for (int f = 0; f < kDetectTileFrames; ++f) {
-        if (f < tf) {
+        for (int f = 0; f < kDetectTileFrames; ++f) {
+          const float p = cur[f * width + tid];
+          const float po = (f >= YC) ? cur[(f - YC) * width + tid] : prev[(f - YC + kDetectTileFrames) * width + tid];
+          const float q = __fsub_rn(p, thr);     // NoiseLearner::work, noise_learner.cpp:54
+          const float old = __fsub_rn(po, thr);  // the row leaving the ring, recomputed
+          sum = __fsub_rn(sum, old);             // Averager::subtract
+          sum = __fadd_rn(sum, q);               // Averager::add
+          const float avg = (a.avg_frames + t0 + f + 1 >= YC) ? div_const<YC>(sum) : kNoData;
+          avg_tile[f * width + tid] = avg;
+          last_avg = avg;
+          if (spec_on) {
+            spec = __fadd_rn(spec, p);
+            const int slot = slot_tile[f];
+            if (slot >= 0) {
+              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+              spec = 0.0f;
+            }
+          }
+        }
+      } else {
+        for (int f = 0; f < tf; ++f) {
           const int t = t0 + f;
           const float p = cur[f * width + tid];
           const bool learning = a.noise_samples + t < a.learn_frames;
@@ -207,13 +255,16 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         float w[SEG + 2 * H];
 #pragma unroll
         for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];
+        float top = -INFINITY;
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {
           float s = w[k];
 #pragma unroll
           for (int i = 1; i <= 2 * H; ++i) s = __fadd_rn(s, w[k + i]);
-          box[k] = __fdiv_rn(s, static_cast<float>(2 * H + 1));
+          box[k] = div_const<2 * H + 1>(s);
+          top = fmaxf(top, box[k]);
         }
+        if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
       } else {
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {

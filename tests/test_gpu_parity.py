@@ -213,6 +213,24 @@ def test_band_matches_oracle_end_to_end(engine, n, fs, frames, learn):
     assert (samples_g, ready_g) == (samples_o, ready_o) and np.max(np.abs(thr_g - thr_o)) <= 2e-3
 
 
+def test_generic_grouping_parameters(engine):
+    """GROUPING_X / GROUPING_Y other than the reference's 21/21 run the generic (runtime-parameter) kernel path."""
+    n, fs, frames, learn = 1024, 2_048_000, 300, 40
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    for gx, gy in ((9, 7), (1, 1), (33, 40)):
+        cfg.grouping_x, cfg.grouping_y = gx, gy
+        band = b2s.Band(engine, cfg)
+        got = band.push(iq, frames, 0, period, per_frame=True, dense=DENSE)
+        ref = ol.OracleChain(cfg).push(iq, frames, 0, period)
+        assert np.max(np.abs(got.avg_db - ref.avg_db)) <= 4e-3 and np.max(np.abs(got.box_db - ref.box_db)) <= 4e-3, (gx, gy)
+        assert _tx(got.frame_tx) == _tx(ref.frame_tx), (gx, gy)
+        cpu = ol.CpuAverager(n, gy, "orc")
+        for k in range(frames):
+            cpu.push(got.noise_sub_db[k])
+        s, a, ring, f = band.get_averager()
+        assert s.tobytes() == cpu.sum()[0].tobytes() and ring.tobytes() == cpu.data().tobytes() and a.tobytes() == cpu.average().tobytes()
+
+
 def test_averager_state_is_bit_exact_on_identical_rows(engine):
     """Feed the oracle's Averager the GPU's own noise-subtracted rows: m_sum, ring, m_average, m_frames and every
     per-frame average row must then be bit-identical (operator-level parity inside the fused chain)."""
@@ -234,6 +252,23 @@ def test_averager_state_is_bit_exact_on_identical_rows(engine):
     # boxcar: serial reference form on the same rows differs from the fused form by rounding only
     ref_box = np.stack([ol.cpu_average(r, cfg.grouping_x) for r in got.avg_db])
     assert np.max(np.abs(got.box_db - ref_box)) <= 1e-3
+
+
+def test_fast_path_equals_dense_path_bitwise(engine):
+    """The specialised steady-state tiles (no dense rows requested) and the generic tiles (dense rows requested) must
+    leave bit-identical Averager state, detections and spectrogram rows."""
+    n, fs, frames, learn = 4096, 2_048_000, 400, 30
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    cfg.spectrogram_interval_ms = 50
+    fast, slow = b2s.Band(engine, cfg), b2s.Band(engine, cfg)
+    gf = fast.push(iq, frames, 0, period, per_frame=True)
+    gs = slow.push(iq, frames, 0, period, per_frame=True, dense=DENSE)
+    assert _tx(gf.frame_tx) == _tx(gs.frame_tx) and gf.n_detect_entries == gs.n_detect_entries > 0
+    for a, b in zip(fast.get_averager(), slow.get_averager()):
+        assert np.array_equal(a, b)
+    tf_, _, rf = fast.get_spectrogram()
+    ts_, _, rs = slow.get_spectrogram()
+    assert np.array_equal(tf_, ts_) and np.array_equal(rf, rs) and len(tf_) >= 2
 
 
 def test_chunked_pushes_equal_one_push(engine):
