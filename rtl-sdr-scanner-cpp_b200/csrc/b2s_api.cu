@@ -389,7 +389,7 @@ struct b2s_band : public DeviceQueries {
         f = end;
       }
       total += w[q].frame_hi - w[q].frame_lo;
-      max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half);
+      max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half + 2 * kBoxSegment);
     }
     int rc = d_work.alloc(work.size());
     if (rc) return rc;

@@ -8,9 +8,11 @@
 //
 // Arithmetic contract: every float operation that feeds Averager state is the reference's operation in the reference's
 // order (separate sub / add / IEEE division, no FMA contraction) so m_sum, the ring and m_average are bit-identical.
-// The frequency boxcar is evaluated as an independent left-to-right window sum per bin (the reference carries ONE
-// running sum across the whole row, a 16384-long serial float chain); the two differ by rounding only (<= ~1e-5 dB,
-// asserted in tests) — b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
+// The frequency boxcar is evaluated per aligned segment of 8 bins: the first bin's window is summed left to right, the
+// next 7 slide it exactly like the reference does (sum -= leaving; sum += entering), see boxcar_segment(). The
+// reference carries ONE running sum across the whole row (a 16384-long serial float chain); restarting it every
+// 8 bins changes rounding only (<= 1e-3 dB vs the reference's own drift, asserted in tests) and keeps the work
+// parallel. b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
 #pragma once
 #include "b2s_device.cuh"
 
@@ -92,7 +94,66 @@ __device__ __forceinline__ float div_const(float x) {
   return __fdiv_rn(x, d);
 }
 
-// boxcar value for bin j from a row of averaged values stored with `halo` extra bins on each side.
+// Same, without the range guard: for callers whose operands are sums of finite dB values (|x| < 2^60 by construction).
+template <int D>
+__device__ __forceinline__ float div_const_fast(float x) {
+  constexpr float d = static_cast<float>(D);
+  constexpr float r = 1.0f / d;
+  const float q = __fmul_rn(x, r);
+  const float e = __fmaf_rn(-q, d, x);
+  return __fmaf_rn(e, r, q);
+}
+
+constexpr int kBoxSegment = 8;  // bins per boxcar segment (segments are aligned to multiples of 8 bins)
+
+// Boxcar of one aligned, interior segment: w[i] holds the averaged value of bin (b0 - H + i), i in [0, 8 + 2H).
+// out[0] = (w[0] + w[1] + ... + w[2H]) / (2H+1) summed left to right; out[k] continues the running sum:
+// s -= w[k-1]; s += w[k+2H]  (utils.cpp:41-48 order: drop the leaving element first, then add the entering one).
+template <int H>
+__device__ __forceinline__ void boxcar_segment(const float (&w)[kBoxSegment + 2 * H], float (&out)[kBoxSegment]) {
+  float s = w[0];
+#pragma unroll
+  for (int i = 1; i <= 2 * H; ++i) s = __fadd_rn(s, w[i]);
+  out[0] = div_const_fast<2 * H + 1>(s);
+#pragma unroll
+  for (int k = 1; k < kBoxSegment; ++k) {
+    s = __fsub_rn(s, w[k - 1]);
+    s = __fadd_rn(s, w[k + 2 * H]);
+    out[k] = div_const_fast<2 * H + 1>(s);
+  }
+}
+// runtime-H version of the same definition (generic instantiations, K3, the stand-alone operator)
+__device__ __forceinline__ void boxcar_segment_rt(const float* w /* bin b0 - half */, int half, float* out) {
+  float s = w[0];
+  for (int i = 1; i <= 2 * half; ++i) s = __fadd_rn(s, w[i]);
+  const float cnt = static_cast<float>(2 * half + 1);
+  out[0] = __fdiv_rn(s, cnt);
+  for (int k = 1; k < kBoxSegment; ++k) {
+    s = __fsub_rn(s, w[k - 1]);
+    s = __fadd_rn(s, w[k + 2 * half]);
+    out[k] = __fdiv_rn(s, cnt);
+  }
+}
+// a segment is interior when none of its 8 windows is clipped by the row ends; clipped segments use boxcar_at per bin
+__device__ __forceinline__ bool segment_interior(int b0, int n, int half) { return half > 0 && b0 - half >= 0 && b0 + kBoxSegment - 1 + half < n; }
+
+// value of ONE bin under the segment definition above, from a row pointer indexed by absolute bin (idx = position of bin j)
+__device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half);
+__device__ __forceinline__ float boxcar_value(const float* a, int idx, int j, int n, int half) {
+  const int b0 = j & ~(kBoxSegment - 1);
+  if (half == 0 && j == n - 1) return 0.0f;  // reference quirk: groupSize 1 never writes the last element (utils.cpp:38)
+  if (!segment_interior(b0, n, half)) return boxcar_at(a, idx, j, n, half);
+  const float* w = a + (idx - (j - b0) - half);
+  float s = w[0];
+  for (int i = 1; i <= 2 * half; ++i) s = __fadd_rn(s, w[i]);
+  for (int k = 1; k <= j - b0; ++k) {
+    s = __fsub_rn(s, w[k - 1]);
+    s = __fadd_rn(s, w[k + 2 * half]);
+  }
+  return __fdiv_rn(s, static_cast<float>(2 * half + 1));
+}
+
+// clipped-window value for bin j (edge segments only) from a row of averaged values stored with `halo` extra bins on each side.
 // a[halo + (i - j0)] holds bin i; bins outside [0, n) are never read.
 __device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half) {
   const int lo = max(0, j - half), hi = min(n - 1, j + half);
@@ -187,7 +248,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
           const float old = __fsub_rn(po, thr);  // the row leaving the ring, recomputed
           sum = __fsub_rn(sum, old);             // Averager::subtract
           sum = __fadd_rn(sum, q);               // Averager::add
-          const float avg = (a.avg_frames + t0 + f + 1 >= YC) ? div_const<YC>(sum) : kNoData;
+          const float avg = (a.avg_frames + t0 + f + 1 >= YC) ? div_const_fast<YC>(sum) : kNoData;
           avg_tile[f * width + tid] = avg;
           last_avg = avg;
           if (spec_on) {
@@ -240,7 +301,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     }
     __syncthreads();
     // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid; one work item = 8 consecutive bins ----
-    constexpr int SEG = 8;
+    constexpr int SEG = kBoxSegment;
     for (int item = tid; item < tf * (kDetectBinsPerCta / SEG); item += kDetectThreads) {
       const int f = item / (kDetectBinsPerCta / SEG), b0 = (item - f * (kDetectBinsPerCta / SEG)) * SEG;
       const int bin0 = j0 + b0;
@@ -248,34 +309,27 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       const int t = t0 + f;
       const float* row = avg_tile + f * width;
       float box[SEG];
-      const bool interior = HALF_T > 0 && bin0 - half >= 0 && bin0 + SEG - 1 + half < n;
-      if (interior) {
-        // same left-to-right window sum as boxcar_at, for 8 bins at once out of one register window
-        constexpr int H = HALF_T > 0 ? HALF_T : 1;
-        float w[SEG + 2 * H];
+      if (segment_interior(bin0, n, half)) {
+        if (HALF_T > 0) {
+          constexpr int H = HALF_T > 0 ? HALF_T : 1;
+          float w[SEG + 2 * H];
 #pragma unroll
-        for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];
-        float top = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < SEG; ++k) {
-          float s = w[k];
-#pragma unroll
-          for (int i = 1; i <= 2 * H; ++i) s = __fadd_rn(s, w[k + i]);
-          box[k] = div_const<2 * H + 1>(s);
-          top = fmaxf(top, box[k]);
+          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];
+          boxcar_segment<H>(w, box);
+        } else {
+          boxcar_segment_rt(row + hp + b0 - half, half, box);
         }
-        if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
+        if (!a.dense_box) {
+          float top = box[0];
+#pragma unroll
+          for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
+          if (top < a.detect_level) continue;  // nothing to report from these 8 bins
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {
           const int bin = bin0 + k;
-          if (bin >= n) {
-            box[k] = -INFINITY;
-          } else if (half == 0 && bin == n - 1) {
-            box[k] = 0.0f;  // reference quirk: with groupSize 1 the last element is never written (utils.cpp:38)
-          } else {
-            box[k] = boxcar_at(row, hp + b0 + k, bin, n, half);
-          }
+          box[k] = (bin >= n) ? -INFINITY : boxcar_value(row, hp + b0 + k, bin, n, half);
         }
       }
 #pragma unroll
@@ -399,7 +453,8 @@ __global__ void __launch_bounds__(256) k_window_query(const WindowArgs a) {
   extern __shared__ float sm[];
   const WindowWork w = a.work[blockIdx.x];
   const int n = a.n, Y = a.group_y, half = a.group_x / 2;
-  const int lo = max(0, w.bin_lo - half), hi = min(n - 1, w.bin_hi + half);
+  // columns needed: the windows of every 8-bin segment that intersects [bin_lo, bin_hi]
+  const int lo = max(0, (w.bin_lo & ~(kBoxSegment - 1)) - half), hi = min(n - 1, (w.bin_hi | (kBoxSegment - 1)) + half);
   const int width = hi - lo + 1;
   float* sum_s = sm;          // [width]
   float* avg_s = sm + width;  // [width]
@@ -429,12 +484,7 @@ __global__ void __launch_bounds__(256) k_window_query(const WindowArgs a) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
       for (int j = w.bin_lo + tid; j <= w.bin_hi; j += blockDim.x) {
-        float box;
-        if (half == 0 && j == n - 1) {
-          box = 0.0f;
-        } else {
-          box = boxcar_at(avg_s, j - lo, j, n, half);
-        }
+        const float box = boxcar_value(avg_s, j - lo, j, n, half);
         argmax_combine(bv, bi, box, j);
       }
       warp_argmax(bv, bi);
@@ -487,7 +537,7 @@ __global__ void k_boxcar(const float* in, float* out, int size, int group, int r
   if (j >= size || r >= rows) return;
   const int half = group / 2;
   const float* row = in + static_cast<size_t>(r) * size;
-  out[static_cast<size_t>(r) * size + j] = (half == 0 && j == size - 1) ? 0.0f : boxcar_at(row, j, j, size, half);
+  out[static_cast<size_t>(r) * size + j] = boxcar_value(row, j, j, size, half);
 }
 
 // average(in, out, size, groupSize), reference form (utils.cpp:31-53): one serial running sum per row, bit-exact.
