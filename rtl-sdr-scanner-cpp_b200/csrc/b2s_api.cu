@@ -622,12 +622,12 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * (kDetectBuffers + 1) * kDetectTileFrames * width + sizeof(int) * kDetectTileFrames;
+    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * kDetectTileFrames;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
     if (profiling) CU(cudaEventRecord(ev[2], stream));

@@ -176,8 +176,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
 // or 0 / -1 for the generic runtime-parameter instantiation. The specialised instantiation runs steady-state tiles
-// (no learning frame in the tile or its look-back, t0 >= Y, full tile, no dense debug rows) through a branch-free,
-// fully unrolled fast path; every other tile takes the generic path. Both paths execute the same float operations.
+// (no learning frame in the tile or its look-back, t0 >= Y, full tile, no dense debug rows) through a fast path that
+// splits the work by dependency: (1a) all threads subtract the noise threshold elementwise, (1b) one thread per
+// column runs ONLY the serial part (m_sum -= leaving; m_sum += entering; m_average = m_sum / Y) out of shared memory,
+// (2) all threads evaluate boxcar + threshold. Every other tile takes the generic per-column path. Both paths execute
+// the same float operations in the same order, so they are interchangeable bit for bit (tested).
 template <int Y_T, int HALF_T>
 __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   extern __shared__ __align__(16) float sm[];
@@ -185,9 +188,11 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
   const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA
   const int tile_elems = kDetectTileFrames * width;
-  float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width]
-  float* __restrict__ avg_tile = sm + kDetectBuffers * tile_elems;  // [TF][width]
-  int* slot_tile = reinterpret_cast<int*>(avg_tile + tile_elems);   // [TF] spectrogram slot of each frame of the tile
+  float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width] raw PSD (cp.async target)
+  float* q_tiles = psd_tiles + kDetectBuffers * tile_elems;         // [2][TF][width] noise-subtracted rows (current, previous)
+  float* __restrict__ avg_tile = q_tiles + 2 * tile_elems;          // [TF][width]
+  float* thr_s = avg_tile + tile_elems;                             // [width]
+  int* slot_tile = reinterpret_cast<int*>(thr_s + width);           // [TF] spectrogram slot of each frame of the tile
 
   const int n = a.n, T = a.n_frames, Y = Y_T > 0 ? Y_T : a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const bool spec_owner = owner && d > 0 && (j % d) == 0;
   float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
   const bool ring_in_smem = Y <= kDetectTileFrames;
+  if (tid < width) thr_s[tid] = thr;
 
   issue_tile(0);
   issue_tile(1);
@@ -231,28 +237,37 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     __syncthreads();
     const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
     const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
+    float* __restrict__ q_cur = q_tiles + (tile & 1) * tile_elems;
+    const float* __restrict__ q_prev = q_tiles + ((tile & 1) ^ 1) * tile_elems;
     // steady state: whole tile, ring look-back inside the push, no learning frame in the tile or in its look-back
-    const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= Y && (a.noise_samples + t0 - Y >= a.learn_frames) && !dense;
+    // (the look-back reads q_prev, which every earlier tile wrote — learning frames as -100 — whichever path it took)
+    const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= kDetectTileFrames && Y <= kDetectTileFrames &&
+                        (a.noise_samples + t0 >= a.learn_frames) && !dense;
 
-    // ---- phase 1: one thread per column marches the tile (noise -> averager) ----
-    if (active) {
-      if (steady) {
+    if (steady) {
+      // ---- phase 1a: NoiseLearner::work (noise_learner.cpp:54) elementwise over the tile, all threads ----
+      for (int e = tid; e < tile_elems; e += kDetectThreads) {
+        const int f = e / width, c = e - f * width;
+        q_cur[e] = __fsub_rn(cur[e], thr_s[c]);
+      }
+      __syncthreads();
+      // ---- phase 1b: the serial part only, one thread per column ----
+      if (active) {
         if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
         constexpr int YC = Y_T > 0 ? Y_T : 1;
         const bool spec_on = (d == 1) && owner;
+        const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize (true from frame Y-1 of the band's life on)
 #pragma unroll
         for (int f = 0; f < kDetectTileFrames; ++f) {
-          const float p = cur[f * width + tid];
-          const float po = (f >= YC) ? cur[(f - YC) * width + tid] : prev[(f - YC + kDetectTileFrames) * width + tid];
-          const float q = __fsub_rn(p, thr);     // NoiseLearner::work, noise_learner.cpp:54
-          const float old = __fsub_rn(po, thr);  // the row leaving the ring, recomputed
-          sum = __fsub_rn(sum, old);             // Averager::subtract
-          sum = __fadd_rn(sum, q);               // Averager::add
-          const float avg = (a.avg_frames + t0 + f + 1 >= YC) ? div_const_fast<YC>(sum) : kNoData;
+          const float q = q_cur[f * width + tid];
+          const float old = (f >= YC) ? q_cur[(f - YC) * width + tid] : q_prev[(f - YC + kDetectTileFrames) * width + tid];
+          sum = __fsub_rn(sum, old);  // Averager::subtract, averager.cpp:46-50
+          sum = __fadd_rn(sum, q);    // Averager::add, averager.cpp:40-44
+          const float avg = full ? div_const_fast<YC>(sum) : kNoData;
           avg_tile[f * width + tid] = avg;
-          last_avg = avg;
+          if (f == kDetectTileFrames - 1) last_avg = avg;
           if (spec_on) {
-            spec = __fadd_rn(spec, p);
+            spec = __fadd_rn(spec, cur[f * width + tid]);  // Spectrogram::process on the RAW row, spectrogram.cpp:46-49
             const int slot = slot_tile[f];
             if (slot >= 0) {
               a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
@@ -260,44 +275,47 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             }
           }
         }
-      } else {
-        for (int f = 0; f < tf; ++f) {
-          const int t = t0 + f;
-          const float p = cur[f * width + tid];
-          const bool learning = a.noise_samples + t < a.learn_frames;
-          if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
-          const float q = noise_sub(p, thr, learning);
-          // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
-          float old;
-          if (t >= Y) {
-            float po;
-            if (ring_in_smem) {
-              po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
-            } else {
-              po = a.psd[static_cast<size_t>(t - Y) * n + j];
-            }
-            old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
+      }
+    } else if (active) {
+      // ---- generic per-column march (learning frames, first tiles of a push, partial tiles, dense debug rows) ----
+      for (int f = 0; f < tf; ++f) {
+        const int t = t0 + f;
+        const float p = cur[f * width + tid];
+        const bool learning = a.noise_samples + t < a.learn_frames;
+        if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
+        const float q = noise_sub(p, thr, learning);
+        q_cur[f * width + tid] = q;  // a later steady tile looks back into this one
+        // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
+        float old;
+        if (t >= Y) {
+          float po;
+          if (ring_in_smem) {
+            po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
           } else {
-            old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
+            po = a.psd[static_cast<size_t>(t - Y) * n + j];
           }
-          if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
-          const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
-          avg_tile[f * width + tid] = avg;
-          last_avg = avg;
-          if (owner) {
-            if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
-            if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
-            if (d == 1) {
-              spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
-              const int slot = slot_tile[f];
-              if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
-                spec = 0.0f;
-              }
+          old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
+        } else {
+          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
+        }
+        if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
+        const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
+        avg_tile[f * width + tid] = avg;
+        last_avg = avg;
+        if (owner) {
+          if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
+          if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
+          if (d == 1) {
+            spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
+            const int slot = slot_tile[f];
+            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+              spec = 0.0f;
             }
           }
         }
       }
+      thr_s[tid] = thr;  // learning may have raised it
     }
     __syncthreads();
     // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid; one work item = 8 consecutive bins ----
