@@ -622,7 +622,8 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * kDetectTileFrames;
+    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * 3 * kDetectTileFrames +
+                        sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {

@@ -20,7 +20,7 @@ namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
-constexpr int kDetectThreads = 256;
+constexpr int kDetectThreads = 512;
 constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
 
@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   float* __restrict__ avg_tile = q_tiles + 2 * tile_elems;          // [TF][width]
   float* thr_s = avg_tile + tile_elems;                             // [width]
   int* slot_tile = reinterpret_cast<int*>(thr_s + width);           // [TF] spectrogram slot of each frame of the tile
+  int* stage_count = slot_tile + kDetectTileFrames;                 // [TF] detection entries staged per frame of the tile
+  int* stage_base = stage_count + kDetectTileFrames;                // [TF] where this CTA's block starts in the frame's slot list
+  DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_base + kDetectTileFrames);  // [TF][kDetectBinsPerCta]
 
   const int n = a.n, T = a.n_frames, Y = Y_T > 0 ? Y_T : a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
   const bool ring_in_smem = Y <= kDetectTileFrames;
   if (tid < width) thr_s[tid] = thr;
+  if (tid < kDetectTileFrames) stage_count[tid] = 0;
 
   issue_tile(0);
   issue_tile(1);
@@ -233,7 +237,9 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     const int t0 = tile * kDetectTileFrames;
     const int tf = min(kDetectTileFrames, T - t0);
     cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
-    if (tid < kDetectTileFrames) slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
+    if (tid < kDetectTileFrames) {
+      slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
+    }
     __syncthreads();
     const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
     const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
@@ -246,9 +252,19 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
 
     if (steady) {
       // ---- phase 1a: NoiseLearner::work (noise_learner.cpp:54) elementwise over the tile, all threads ----
-      for (int e = tid; e < tile_elems; e += kDetectThreads) {
-        const int f = e / width, c = e - f * width;
-        q_cur[e] = __fsub_rn(cur[e], thr_s[c]);
+      if (width <= 160) {
+        constexpr int G = kDetectThreads / 160;  // frame groups marching side by side
+        const int c = tid % 160, g = tid / 160;
+        if (c < width && g < G) {
+          const float th = thr_s[c];
+#pragma unroll 4
+          for (int f = g; f < kDetectTileFrames; f += G) q_cur[f * width + c] = __fsub_rn(cur[f * width + c], th);
+        }
+      } else {
+        for (int e = tid; e < tile_elems; e += kDetectThreads) {
+          const int f = e / width, c = e - f * width;
+          q_cur[e] = __fsub_rn(cur[e], thr_s[c]);
+        }
       }
       __syncthreads();
       // ---- phase 1b: the serial part only, one thread per column ----
@@ -356,8 +372,8 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         if (bin < n) {
           if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
           if (box[k] >= a.detect_level) {
-            const int pos = atomicAdd(a.slot_count + t, 1);
-            if (pos < a.slot_capacity) a.slots[static_cast<size_t>(t) * a.slot_capacity + pos] = DetectEntry{bin, box[k]};
+            const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
+            stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
           }
         }
       }
@@ -376,6 +392,20 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     }
     __syncthreads();       // everyone is done with tile-1's buffer (ring look-back) and with avg_tile / slot_tile
     issue_tile(tile + 2);  // reuses the buffer of tile-1
+    // flush the staged detection entries: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list
+    if (tid < tf) {
+      const int cnt = stage_count[tid];
+      stage_base[tid] = cnt > 0 ? atomicAdd(a.slot_count + t0 + tid, cnt) : 0;
+    }
+    __syncthreads();
+    for (int f = tid >> 5; f < tf; f += kDetectThreads >> 5) {  // one warp per frame
+      const int cnt = stage_count[f], base = stage_base[f];
+      for (int i = tid & 31; i < cnt; i += 32) {
+        if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + f) * a.slot_capacity + base + i] = stage[f * kDetectBinsPerCta + i];
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) stage_count[f] = 0;  // re-armed for the next tile (phase 2 of which is two barriers away)
+    }
   }
   cp_async_wait<0>();
 
