@@ -14,6 +14,8 @@
 // 8 bins changes rounding only (<= 1e-3 dB vs the reference's own drift, asserted in tests) and keeps the work
 // parallel. b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
 #pragma once
+#include <cstdio>
+
 #include "b2s_device.cuh"
 
 namespace b2s {
@@ -106,60 +108,41 @@ __device__ __forceinline__ float div_const_fast(float x) {
 
 constexpr int kBoxSegment = 8;  // bins per boxcar segment (segments are aligned to multiples of 8 bins)
 
-// Boxcar of one aligned, interior segment: w[i] holds the averaged value of bin (b0 - H + i), i in [0, 8 + 2H).
-// out[0] = (w[0] + w[1] + ... + w[2H]) / (2H+1) summed left to right; out[k] continues the running sum:
-// s -= w[k-1]; s += w[k+2H]  (utils.cpp:41-48 order: drop the leaving element first, then add the entering one).
+// Boxcar running sums of one aligned segment of 8 bins over the ZERO-EXTENDED row: w[i] holds the averaged value of bin
+// (b0 - H + i), i in [0, 8 + 2H), with 0.0f wherever that bin lies outside [0, N) (adding or subtracting 0.0f is exact,
+// so clipped windows come out as the left-to-right sum of their valid bins). sums[0] = w[0] + w[1] + ... + w[2H];
+// sums[k] continues the running sum exactly like utils.cpp:41-48: drop the leaving element, then add the entering one.
 template <int H>
-__device__ __forceinline__ void boxcar_segment(const float (&w)[kBoxSegment + 2 * H], float (&out)[kBoxSegment]) {
+__device__ __forceinline__ void boxcar_segment(const float (&w)[kBoxSegment + 2 * H], float (&sums)[kBoxSegment]) {
   float s = w[0];
 #pragma unroll
   for (int i = 1; i <= 2 * H; ++i) s = __fadd_rn(s, w[i]);
-  out[0] = div_const_fast<2 * H + 1>(s);
+  sums[0] = s;
 #pragma unroll
   for (int k = 1; k < kBoxSegment; ++k) {
     s = __fsub_rn(s, w[k - 1]);
     s = __fadd_rn(s, w[k + 2 * H]);
-    out[k] = div_const_fast<2 * H + 1>(s);
+    sums[k] = s;
   }
 }
-// runtime-H version of the same definition (generic instantiations, K3, the stand-alone operator)
-__device__ __forceinline__ void boxcar_segment_rt(const float* w /* bin b0 - half */, int half, float* out) {
-  float s = w[0];
-  for (int i = 1; i <= 2 * half; ++i) s = __fadd_rn(s, w[i]);
-  const float cnt = static_cast<float>(2 * half + 1);
-  out[0] = __fdiv_rn(s, cnt);
-  for (int k = 1; k < kBoxSegment; ++k) {
-    s = __fsub_rn(s, w[k - 1]);
-    s = __fadd_rn(s, w[k + 2 * half]);
-    out[k] = __fdiv_rn(s, cnt);
-  }
-}
-// a segment is interior when none of its 8 windows is clipped by the row ends; clipped segments use boxcar_at per bin
-__device__ __forceinline__ bool segment_interior(int b0, int n, int half) { return half > 0 && b0 - half >= 0 && b0 + kBoxSegment - 1 + half < n; }
+// number of valid bins in the window of bin j (the reference's `count`, utils.cpp:34-49)
+__device__ __forceinline__ int boxcar_count(int j, int n, int half) { return min(n - 1, j + half) - max(0, j - half) + 1; }
+// a segment is interior when none of its 8 windows is clipped by the row ends (then every count is 2*half + 1)
+__device__ __forceinline__ bool segment_interior(int b0, int n, int half) { return b0 - half >= 0 && b0 + kBoxSegment - 1 + half < n; }
 
-// value of ONE bin under the segment definition above, from a row pointer indexed by absolute bin (idx = position of bin j)
-__device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half);
-__device__ __forceinline__ float boxcar_value(const float* a, int idx, int j, int n, int half) {
-  const int b0 = j & ~(kBoxSegment - 1);
+// Boxcar value of ONE bin under the same definition, for any half; `at(bin)` returns the averaged value of a valid bin.
+template <typename At>
+__device__ __forceinline__ float boxcar_value(At at, int j, int n, int half) {
   if (half == 0 && j == n - 1) return 0.0f;  // reference quirk: groupSize 1 never writes the last element (utils.cpp:38)
-  if (!segment_interior(b0, n, half)) return boxcar_at(a, idx, j, n, half);
-  const float* w = a + (idx - (j - b0) - half);
-  float s = w[0];
-  for (int i = 1; i <= 2 * half; ++i) s = __fadd_rn(s, w[i]);
+  const int b0 = j & ~(kBoxSegment - 1);
+  auto z = [&](int bin) { return (bin >= 0 && bin < n) ? at(bin) : 0.0f; };
+  float s = z(b0 - half);
+  for (int i = 1; i <= 2 * half; ++i) s = __fadd_rn(s, z(b0 - half + i));
   for (int k = 1; k <= j - b0; ++k) {
-    s = __fsub_rn(s, w[k - 1]);
-    s = __fadd_rn(s, w[k + 2 * half]);
+    s = __fsub_rn(s, z(b0 - half + k - 1));
+    s = __fadd_rn(s, z(b0 + half + k));
   }
-  return __fdiv_rn(s, static_cast<float>(2 * half + 1));
-}
-
-// clipped-window value for bin j (edge segments only) from a row of averaged values stored with `halo` extra bins on each side.
-// a[halo + (i - j0)] holds bin i; bins outside [0, n) are never read.
-__device__ __forceinline__ float boxcar_at(const float* a, int idx, int j, int n, int half) {
-  const int lo = max(0, j - half), hi = min(n - 1, j + half);
-  float s = a[idx + (lo - j)];
-  for (int i = lo + 1; i <= hi; ++i) s = __fadd_rn(s, a[idx + (i - j)]);
-  return __fdiv_rn(s, static_cast<float>(hi - lo + 1));
+  return __fdiv_rn(s, static_cast<float>(boxcar_count(j, n, half)));
 }
 
 // 16-byte asynchronous global->shared copy (LDGSTS); used to stream PSD tiles ahead of the march
@@ -230,13 +213,24 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const bool ring_in_smem = Y <= kDetectTileFrames;
   if (tid < width) thr_s[tid] = thr;
   if (tid < kDetectTileFrames) stage_count[tid] = 0;
+  if (tid < width && !active) {  // columns outside the row: the boxcar sees the zero-extended row
+    for (int f = 0; f < kDetectTileFrames; ++f) avg_tile[f * width + tid] = 0.0f;
+  }
 
+#ifdef B2S_K2_TIMING
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  long long c0 = clock64();
+#define TK(i) { long long c1 = clock64(); tk[i] += c1 - c0; c0 = c1; }
+#else
+#define TK(i)
+#endif
   issue_tile(0);
   issue_tile(1);
   for (int tile = 0; tile < n_tiles; ++tile) {
     const int t0 = tile * kDetectTileFrames;
     const int tf = min(kDetectTileFrames, T - t0);
     cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
+    TK(0)
     if (tid < kDetectTileFrames) {
       slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
     }
@@ -251,45 +245,48 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
                         (a.noise_samples + t0 >= a.learn_frames) && !dense;
 
     if (steady) {
-      // ---- phase 1a: NoiseLearner::work (noise_learner.cpp:54) elementwise over the tile, all threads ----
-      if (width <= 160) {
-        constexpr int G = kDetectThreads / 160;  // frame groups marching side by side
-        const int c = tid % 160, g = tid / 160;
-        if (c < width && g < G) {
-          const float th = thr_s[c];
-#pragma unroll 4
-          for (int f = g; f < kDetectTileFrames; f += G) q_cur[f * width + c] = __fsub_rn(cur[f * width + c], th);
-        }
-      } else {
-        for (int e = tid; e < tile_elems; e += kDetectThreads) {
-          const int f = e / width, c = e - f * width;
-          q_cur[e] = __fsub_rn(cur[e], thr_s[c]);
-        }
-      }
-      __syncthreads();
-      // ---- phase 1b: the serial part only, one thread per column ----
+      // ---- phase 1 (fast): one thread per column. All shared-memory loads of the tile are issued up front and kept
+      // in registers; the only serial work left is m_sum -= leaving; m_sum += entering (2 dependent FADDs per frame) ----
       if (active) {
         if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
         constexpr int YC = Y_T > 0 ? Y_T : 1;
-        const bool spec_on = (d == 1) && owner;
-        const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize (true from frame Y-1 of the band's life on)
+        constexpr int TF = kDetectTileFrames;
+        const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize
+        float q[TF], lead[YC];
 #pragma unroll
-        for (int f = 0; f < kDetectTileFrames; ++f) {
-          const float q = q_cur[f * width + tid];
-          const float old = (f >= YC) ? q_cur[(f - YC) * width + tid] : q_prev[(f - YC + kDetectTileFrames) * width + tid];
-          sum = __fsub_rn(sum, old);  // Averager::subtract, averager.cpp:46-50
-          sum = __fadd_rn(sum, q);    // Averager::add, averager.cpp:40-44
-          const float avg = full ? div_const_fast<YC>(sum) : kNoData;
-          avg_tile[f * width + tid] = avg;
-          if (f == kDetectTileFrames - 1) last_avg = avg;
-          if (spec_on) {
-            spec = __fadd_rn(spec, cur[f * width + tid]);  // Spectrogram::process on the RAW row, spectrogram.cpp:46-49
-            const int slot = slot_tile[f];
-            if (slot >= 0) {
-              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
-              spec = 0.0f;
+        for (int f = 0; f < TF; ++f) q[f] = cur[f * width + tid];
+#pragma unroll
+        for (int f = 0; f < YC; ++f) lead[f] = q_prev[(f - YC + TF) * width + tid];  // rows leaving the ring during the first Y frames
+        // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49); a row is emitted at most once per tile
+        if (d == 1 && owner) {
+          int emit = -1;
+#pragma unroll
+          for (int f = 0; f < TF; ++f) emit = (slot_tile[f] >= 0 && emit < 0) ? f : emit;
+          if (emit < 0) {
+#pragma unroll
+            for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, q[f]);
+          } else {
+            for (int f = 0; f < TF; ++f) {
+              spec = __fadd_rn(spec, cur[f * width + tid]);
+              const int slot = slot_tile[f];
+              if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72
+                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+                spec = 0.0f;
+              }
             }
           }
+        }
+#pragma unroll
+        for (int f = 0; f < TF; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+          const float old = (f >= YC) ? q[f - YC] : lead[f];
+          sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
+          sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
+          const float avg = full ? div_const_fast<YC>(sum) : kNoData;
+          avg_tile[f * width + tid] = avg;
+          q_cur[f * width + tid] = q[f];  // the next tile looks back into this one
+          if (f == TF - 1) last_avg = avg;
         }
       }
     } else if (active) {
@@ -334,6 +331,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       thr_s[tid] = thr;  // learning may have raised it
     }
     __syncthreads();
+    TK(2)
     // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid; one work item = 8 consecutive bins ----
     constexpr int SEG = kBoxSegment;
     for (int item = tid; item < tf * (kDetectBinsPerCta / SEG); item += kDetectThreads) {
@@ -343,28 +341,31 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       const int t = t0 + f;
       const float* row = avg_tile + f * width;
       float box[SEG];
-      if (segment_interior(bin0, n, half)) {
-        if (HALF_T > 0) {
-          constexpr int H = HALF_T > 0 ? HALF_T : 1;
-          float w[SEG + 2 * H];
+      if (HALF_T > 0) {
+        constexpr int H = HALF_T > 0 ? HALF_T : 1;
+        float w[SEG + 2 * H];
 #pragma unroll
-          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];
-          boxcar_segment<H>(w, box);
+        for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];  // columns outside [0, N) hold 0.0f
+        boxcar_segment<H>(w, box);
+        if (segment_interior(bin0, n, half)) {
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) box[k] = div_const_fast<2 * H + 1>(box[k]);
         } else {
-          boxcar_segment_rt(row + hp + b0 - half, half, box);
-        }
-        if (!a.dense_box) {
-          float top = box[0];
 #pragma unroll
-          for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
-          if (top < a.detect_level) continue;  // nothing to report from these 8 bins
+          for (int k = 0; k < SEG; ++k) box[k] = __fdiv_rn(box[k], static_cast<float>(boxcar_count(bin0 + k, n, half)));
         }
       } else {
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {
           const int bin = bin0 + k;
-          box[k] = (bin >= n) ? -INFINITY : boxcar_value(row, hp + b0 + k, bin, n, half);
+          box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return row[hp + (bb - j0)]; }, bin, n, half);
         }
+      }
+      if (!a.dense_box) {
+        float top = box[0];
+#pragma unroll
+        for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
+        if (top < a.detect_level) continue;  // nothing to report from these 8 bins
       }
 #pragma unroll
       for (int k = 0; k < SEG; ++k) {
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       }
     }
     __syncthreads();       // everyone is done with tile-1's buffer (ring look-back) and with avg_tile / slot_tile
+    TK(3)
     issue_tile(tile + 2);  // reuses the buffer of tile-1
     // flush the staged detection entries: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list
     if (tid < tf) {
@@ -406,8 +408,15 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       __syncwarp();
       if ((tid & 31) == 0) stage_count[f] = 0;  // re-armed for the next tile (phase 2 of which is two barriers away)
     }
+    TK(4)
   }
   cp_async_wait<0>();
+#ifdef B2S_K2_TIMING
+  if ((tid == 0 || tid == 300) && (blockIdx.x % 32 == 3 || blockIdx.x == 83 || blockIdx.x == 0 || blockIdx.x == 127 || blockIdx.x == 24) && T > 1000) {
+    printf("cta %3d tid %3d per-tile cycles: wait %6lld | 1a %6lld | 1b %6lld | ph2 %6lld | flush %6lld\n", blockIdx.x, tid, tk[0] / n_tiles, tk[1] / n_tiles, tk[2] / n_tiles,
+           tk[3] / n_tiles, tk[4] / n_tiles);
+  }
+#endif
 
   if (owner) {
     a.threshold[j] = thr;
@@ -532,7 +541,7 @@ __global__ void __launch_bounds__(256) k_window_query(const WindowArgs a) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
       for (int j = w.bin_lo + tid; j <= w.bin_hi; j += blockDim.x) {
-        const float box = boxcar_value(avg_s, j - lo, j, n, half);
+        const float box = boxcar_value([&](int bb) { return avg_s[bb - lo]; }, j, n, half);
         argmax_combine(bv, bi, box, j);
       }
       warp_argmax(bv, bi);
@@ -578,14 +587,14 @@ __global__ void k_averager_push(const float* rows, int count, int size, int grou
   }
 }
 
-// average(in, out, size, groupSize), engine form: independent window sums (same boxcar_at as k_detect)
+// average(in, out, size, groupSize), engine form: zero-extended 8-bin segments (same definition as k_detect)
 __global__ void k_boxcar(const float* in, float* out, int size, int group, int rows) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   if (j >= size || r >= rows) return;
   const int half = group / 2;
   const float* row = in + static_cast<size_t>(r) * size;
-  out[static_cast<size_t>(r) * size + j] = boxcar_value(row, j, j, size, half);
+  out[static_cast<size_t>(r) * size + j] = boxcar_value([&](int bb) { return row[bb]; }, j, size, half);
 }
 
 // average(in, out, size, groupSize), reference form (utils.cpp:31-53): one serial running sum per row, bit-exact.
