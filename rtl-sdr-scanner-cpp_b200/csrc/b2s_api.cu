@@ -264,7 +264,9 @@ struct b2s_band : public DeviceQueries {
   int slot_capacity = 0;  // detection entries per frame
 
   SpectralTables tables;
-  DevBuf<unsigned char> d_iq;
+  DevBuf<unsigned char> d_iq[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
   DevBuf<float> d_psd, d_lin, d_dense_q, d_dense_avg, d_dense_box;
   DevBuf<int> d_peak_idx;
   DevBuf<float> d_peak_val;
@@ -301,13 +303,17 @@ struct b2s_band : public DeviceQueries {
 
   ~b2s_band() {
     tables.release();
-    d_iq.release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
+    d_iq[0].release(); d_iq[1].release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
     d_peak_idx.release(); d_peak_val.release(); d_sum.release(); d_ring[0].release(); d_ring[1].release(); d_avg_last.release();
     d_ckpt.release(); d_slots.release(); d_sorted.release(); d_slot_count.release(); d_offsets.release(); d_max_count.release(); h_offsets.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
     d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
     for (auto& kv : noise) kv.second.threshold.release();
     for (auto& kv : spectro) kv.second.sum.release();
     for (auto& e : ev) {
+      if (e) cudaEventDestroy(e);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto& e : copy_done) {
       if (e) cudaEventDestroy(e);
     }
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -860,22 +866,53 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
   const size_t bytes_per_sample = b->cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
   const size_t stride_bytes = static_cast<size_t>(b->cfg.frame_stride_samples) * bytes_per_sample;
   const bool on_device = (b->cfg.flags & B2S_FLAG_IQ_ON_DEVICE) != 0;
-  for (size_t done = 0; done < n_frames;) {
-    const size_t chunk = std::min(n_frames - done, static_cast<size_t>(b->max_frames));
-    const char* src = static_cast<const char*>(iq) + done * stride_bytes;
-    const void* dev = src;
-    if (!on_device) {
-      // last frame only needs N samples, not a whole stride
-      const size_t bytes = (chunk - 1) * stride_bytes + static_cast<size_t>(b->cfg.fft_size) * bytes_per_sample;
-      int rc = b->d_iq.alloc(static_cast<size_t>(b->max_frames) * stride_bytes);
+  if (on_device) {
+    for (size_t done = 0; done < n_frames;) {
+      const size_t chunk = std::min(n_frames - done, static_cast<size_t>(b->max_frames));
+      int rc = b->push_chunk(static_cast<const char*>(iq) + done * stride_bytes, chunk, t0_ms, frame_period_ms, done, out);
       if (rc) return rc;
-      CU(cudaMemcpyAsync(b->d_iq.p, src, bytes, cudaMemcpyHostToDevice, b->stream));
-      b->prof.h2d_bytes += bytes;
-      dev = b->d_iq.p;
+      done += chunk;
     }
-    int rc = b->push_chunk(dev, chunk, t0_ms, frame_period_ms, done, out);
+    return 0;
+  }
+  // Host input: the push is cut into pipeline chunks; the host->device copy of chunk i+1 runs on a second stream
+  // while chunk i is in the kernels / tracker (double-buffered staging), so PCIe time hides behind compute (or vice versa).
+  const size_t pipe = std::max<size_t>(1, std::min<size_t>(b->max_frames, n_frames >= 512 ? (n_frames + 3) / 4 : n_frames));
+  if (!b->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&b->copy_done[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->copy_done[1], cudaEventDisableTiming));
+  }
+  const size_t buf_bytes = pipe * stride_bytes;
+  for (int i = 0; i < 2; ++i) {
+    int rc = b->d_iq[i].alloc(buf_bytes);
+    if (rc) return rc;
+  }
+  auto chunk_len = [&](size_t done) { return std::min(n_frames - done, pipe); };
+  auto start_copy = [&](size_t done, int slot) -> int {
+    const size_t chunk = chunk_len(done);
+    const size_t bytes = (chunk - 1) * stride_bytes + static_cast<size_t>(b->cfg.fft_size) * bytes_per_sample;  // the last frame needs N samples only
+    CU(cudaMemcpyAsync(b->d_iq[slot].p, static_cast<const char*>(iq) + done * stride_bytes, bytes, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaEventRecord(b->copy_done[slot], b->copy_stream));
+    b->prof.h2d_bytes += bytes;
+    return 0;
+  };
+  int slot = 0;
+  if (n_frames > 0) {
+    int rc = start_copy(0, 0);
+    if (rc) return rc;
+  }
+  for (size_t done = 0; done < n_frames;) {
+    const size_t chunk = chunk_len(done);
+    CU(cudaStreamWaitEvent(b->stream, b->copy_done[slot], 0));
+    if (done + chunk < n_frames) {  // the other staging buffer was released when the previous chunk finished (push_chunk is synchronous)
+      int rc = start_copy(done + chunk, slot ^ 1);
+      if (rc) return rc;
+    }
+    int rc = b->push_chunk(b->d_iq[slot].p, chunk, t0_ms, frame_period_ms, done, out);
     if (rc) return rc;
     done += chunk;
+    slot ^= 1;
   }
   return 0;
 }
