@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -282,6 +283,7 @@ struct b2s_band : public DeviceQueries {
   DevBuf<int> d_wq_idx;
   PinBuf<DetectEntry> h_entries;
   PinBuf<int> h_small, h_offsets;
+  PinBuf<WindowWork> h_work;
 
   std::map<int32_t, NoiseSlot> noise;
   std::map<int32_t, SpectroSlot> spectro;
@@ -305,7 +307,7 @@ struct b2s_band : public DeviceQueries {
     tables.release();
     d_iq[0].release(); d_iq[1].release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
     d_peak_idx.release(); d_peak_val.release(); d_sum.release(); d_ring[0].release(); d_ring[1].release(); d_avg_last.release();
-    d_ckpt.release(); d_slots.release(); d_sorted.release(); d_slot_count.release(); d_offsets.release(); d_max_count.release(); h_offsets.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
+    d_ckpt.release(); d_slots.release(); d_sorted.release(); d_slot_count.release(); d_offsets.release(); d_max_count.release(); h_offsets.release(); h_work.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
     d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
     for (auto& kv : noise) kv.second.threshold.release();
     for (auto& kv : spectro) kv.second.sum.release();
@@ -397,11 +399,15 @@ struct b2s_band : public DeviceQueries {
       total += w[q].frame_hi - w[q].frame_lo;
       max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half + 2 * kBoxSegment);
     }
-    int rc = d_work.alloc(work.size());
+    // the (small) work list stays in pinned host memory and is read by the kernel through its device alias: a
+    // host->device copy here would queue behind the bulk IQ copy of the next pipeline chunk
+    int rc = h_work.alloc(work.size());
     if (rc) return rc;
     if ((rc = d_wq_val.alloc(total))) return rc;
     if ((rc = d_wq_idx.alloc(total))) return rc;
-    CU(cudaMemcpyAsync(d_work.p, work.data(), sizeof(WindowWork) * work.size(), cudaMemcpyHostToDevice, stream));
+    std::memcpy(h_work.p, work.data(), sizeof(WindowWork) * work.size());
+    WindowWork* work_dev = nullptr;
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&work_dev), h_work.p, 0));
     NoiseSlot* ns = nullptr;
     if ((rc = noise_slot(&ns))) return rc;
     WindowArgs a{};
@@ -415,7 +421,7 @@ struct b2s_band : public DeviceQueries {
     a.ring_in = d_ring[ring_cur ^ 1].p;
     a.avg_frames = cur_avg_frames_before;
     a.checkpoints = d_ckpt.p;
-    a.work = d_work.p;
+    a.work = work_dev;
     a.out_value = d_wq_val.p;
     a.out_index = d_wq_idx.p;
     const size_t smem = sizeof(float) * 2 * max_width;
@@ -436,7 +442,6 @@ struct b2s_band : public DeviceQueries {
     CU(cudaMemcpyAsync(ix.data(), d_wq_idx.p, sizeof(int) * total, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     prof.d2h_bytes += (sizeof(float) + sizeof(int)) * total;
-    prof.h2d_bytes += sizeof(WindowWork) * work.size();
     if (profiling) {
       float ms = 0.0f;
       CU(cudaEventElapsedTime(&ms, w0, w1));
@@ -555,6 +560,7 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
 
   // ---- plan the spectrogram emissions of this chunk from the clock (Spectrogram::send, spectrogram.cpp:62-75) ----
   int n_slots = 0;
+  int emit_frames[kMaxSpecEmits] = {0}, emit_divs[kMaxSpecEmits] = {0};
   SpectroSlot* ss = nullptr;
   const int M = cfg.spectrogram_out_size;
   std::vector<int64_t> slot_time;
@@ -568,28 +574,20 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
       it->second.last_send = host::frame_time(t0_ms, period_ms, frame_offset);  // Container ctor: getTime()
     }
     ss = &it->second;
-    int* slots = h_small.p;
-    std::vector<int> divs;
     for (int t = 0; t < T; ++t) {
       const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
       ss->counter++;
       if (ss->last_send + cfg.spectrogram_interval_ms < now) {
-        slots[t] = n_slots++;
-        divs.push_back(ss->counter);
+        if (n_slots >= kMaxSpecEmits) return fail(B2S_E_INVALID, "more than %d spectrogram rows fall into one push chunk; push fewer frames or raise the interval", kMaxSpecEmits);
+        emit_frames[n_slots] = t;
+        emit_divs[n_slots] = ss->counter;
+        ++n_slots;
         slot_time.push_back(now);
         ss->counter = 0;
         ss->last_send = now;
-      } else {
-        slots[t] = -1;
       }
     }
-    CU(cudaMemcpyAsync(d_spec_slot.p, slots, sizeof(int) * T, cudaMemcpyHostToDevice, stream));
-    if (n_slots > 0) {
-      if ((rc = d_spec_div.alloc(n_slots))) return rc;
-      if ((rc = d_spec_rows.alloc(static_cast<size_t>(n_slots) * M))) return rc;
-      CU(cudaMemcpyAsync(d_spec_div.p, divs.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, stream));
-      CU(cudaStreamSynchronize(stream));  // divs is a local vector
-    }
+    if (n_slots > 0 && (rc = d_spec_rows.alloc(static_cast<size_t>(n_slots) * M))) return rc;
   }
 
   // ---- K2: noise / averager / boxcar / detect / spectrogram ----
@@ -618,8 +616,11 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   da.slot_capacity = slot_capacity;
   da.spec_out = M;
   da.spec_sum = ss ? ss->sum.p : nullptr;
-  da.spec_slot = d_spec_slot.p;
-  da.spec_div = d_spec_div.p;
+  da.n_emit = n_slots;
+  for (int i = 0; i < n_slots; ++i) {
+    da.emit_frame[i] = emit_frames[i];
+    da.emit_div[i] = emit_divs[i];
+  }
   da.spec_rows = d_spec_rows.p;
   da.dense_q = want_dense_q ? d_dense_q.p : nullptr;
   da.dense_avg = want_dense_avg ? d_dense_avg.p : nullptr;
@@ -671,7 +672,6 @@ int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, doubl
   CU(cudaMemcpyAsync(h_max, d_max_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
   const int n_entries = h_off[T];
-  prof.pushes += 1;
   prof.frames += T;
   prof.spectral_launches += 1;
   prof.detect_launches += 1;  // k_detect (+ the two small list-ordering kernels, timed with it)
@@ -863,6 +863,7 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
     out->n_detect_entries = 0;
     out->n_spectrogram_rows = 0;
   }
+  b->prof.pushes += 1;
   const size_t bytes_per_sample = b->cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
   const size_t stride_bytes = static_cast<size_t>(b->cfg.frame_stride_samples) * bytes_per_sample;
   const bool on_device = (b->cfg.flags & B2S_FLAG_IQ_ON_DEVICE) != 0;
@@ -898,21 +899,46 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
     return 0;
   };
   int slot = 0;
+  const bool trace = getenv("B2S_TRACE") != nullptr;
+  cudaEvent_t tr[32];
+  int ntr = 0;
+  auto mark = [&](cudaStream_t st) {
+    if (trace && ntr < 32) {
+      cudaEventCreate(&tr[ntr]);
+      cudaEventRecord(tr[ntr], st);
+      ++ntr;
+    }
+  };
   if (n_frames > 0) {
+    mark(b->copy_stream);
     int rc = start_copy(0, 0);
     if (rc) return rc;
+    mark(b->copy_stream);
   }
   for (size_t done = 0; done < n_frames;) {
     const size_t chunk = chunk_len(done);
     CU(cudaStreamWaitEvent(b->stream, b->copy_done[slot], 0));
     if (done + chunk < n_frames) {  // the other staging buffer was released when the previous chunk finished (push_chunk is synchronous)
+      mark(b->copy_stream);
       int rc = start_copy(done + chunk, slot ^ 1);
       if (rc) return rc;
+      mark(b->copy_stream);
     }
+    mark(b->stream);
     int rc = b->push_chunk(b->d_iq[slot].p, chunk, t0_ms, frame_period_ms, done, out);
     if (rc) return rc;
+    mark(b->stream);
     done += chunk;
     slot ^= 1;
+  }
+  if (trace) {
+    cudaDeviceSynchronize();
+    for (int i = 1; i < ntr; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tr[0], tr[i]);
+      fprintf(stderr, "trace[%d] %.3f ms\n", i, ms);
+    }
+    for (int i = 0; i < ntr; ++i) cudaEventDestroy(tr[i]);
   }
   return 0;
 }

@@ -24,6 +24,7 @@ constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the large
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
 constexpr int kDetectThreads = 512;
 constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
+constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
 
 struct DetectEntry {  // one bin whose boxcar power reached min(start, stop) in one frame
@@ -58,9 +59,12 @@ struct DetectArgs {
   // spectrogram
   int spec_out;           // M (0 = off)
   float* spec_sum;        // [M]
-  const int* spec_slot;   // [T] -1, or the output row to emit after accumulating this frame (host-planned from the clock)
-  const int* spec_div;    // [slots] Container::m_counter at the moment row `slot` is emitted
-  signed char* spec_rows; // [slots][M]
+  // rows to emit during this push, planned by the host from the frame clock (Spectrogram::send, spectrogram.cpp:62-75).
+  // Carried in the kernel arguments so that no small host->device copy sits on the critical path behind the bulk IQ copy.
+  int n_emit;                      // <= kMaxSpecEmits
+  int emit_frame[kMaxSpecEmits];   // frame after which row i is emitted (ascending)
+  int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
+  signed char* spec_rows;          // [n_emit][M]
   // optional dense rows [T][N]
   float* dense_q;
   float* dense_avg;
@@ -232,7 +236,11 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
     TK(0)
     if (tid < kDetectTileFrames) {
-      slot_tile[tid] = (d > 0 && t0 + tid < T) ? a.spec_slot[t0 + tid] : -1;
+      int slot = -1;
+      if (d > 0) {
+        for (int i = 0; i < a.n_emit; ++i) slot = (a.emit_frame[i] == t0 + tid) ? i : slot;
+      }
+      slot_tile[tid] = slot;
     }
     __syncthreads();
     const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
               spec = __fadd_rn(spec, cur[f * width + tid]);
               const int slot = slot_tile[f];
               if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72
-                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
                 spec = 0.0f;
               }
             }
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
             const int slot = slot_tile[f];
             if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
               spec = 0.0f;
             }
           }
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));               // spectrogram.cpp:57
         const int slot = slot_tile[f];
         if (slot >= 0) {
-          a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.spec_div[slot]))));
+          a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
           spec = 0.0f;
         }
       }
