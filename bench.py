@@ -40,6 +40,11 @@ SAMPLE_RATE = 20_000_000
 FRAMES = 4096
 LEARN = 100
 ALG_BYTES_PER_SAMPLE = 6.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_spectrum<16384> launch of this workload, from the committed
+# `ncu --set full` capture profiles/r01_k1_v1.1_ncu_summary.txt (134.5 MB read + 209.3 MB written; part of the 268 MB of
+# rows is still dirty in the 126 MB L2 when the kernel ends)
+K1_DRAM_TRAFFIC_BYTES = 343.8e6
+K1_TRAFFIC_SOURCE = "profiles/r01_k1_v1.1_ncu_summary.txt"
 METRIC = "IQ MSamples/s through FFT+power+detect"
 
 
@@ -53,6 +58,28 @@ def bench_tones(synth, n_fft, frames, learn):
         synth.Tone(0.055 * n_fft / 2 + 0.1, amplitude=40.0, fm_dev_bins=5.0, on_frames=[(a + int(0.10 * span), a + int(0.45 * span))], phase=1.0),
         synth.Tone(-0.17 * n_fft / 2 + 0.1, amplitude=40.0, fm_dev_bins=5.0, on_frames=[(a + int(0.40 * span), a + int(0.95 * span))], phase=2.0),
     ]
+
+
+def bands_for_rank(n_bands: int, rank: int, world: int):
+    """SURVEY.md §8e partitioning: band b lives on GPU b mod G; frames of a band never leave their GPU."""
+    return [b for b in range(n_bands) if b % world == rank]
+
+
+def reduce_step_time(ms_local: float, device=None) -> float:
+    """Max over ranks of the device-timed region (the slowest rank defines the step); identity for one rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(ms_local)
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_msps(samples_per_rank_step: int, steps: int, world: int, ms_max: float) -> float:
+    """Whole-job throughput: all ranks' samples over the slowest rank's time."""
+    return world * samples_per_rank_step * steps / (ms_max / 1000.0) / 1e6
 
 
 def measured_peaks():
@@ -229,16 +256,13 @@ def main():
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
         prof = band.get_profile(reset=True)
-        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        return float(tms.item()), prof, clocks, last, res.n_detect_entries
+        return reduce_step_time(ms, dev), prof, clocks, last, res.n_detect_entries
 
     # ---- device-resident run (value + roofline) ----
     band = make_band(b2s.FLAG_IQ_ON_DEVICE)
     ms, prof, clocks, n_tx, n_ent = timed(band, iq_dev.data_ptr(), args.steps, args.warmup, "device")
     samples_step = T * N_FFT
-    value = world * samples_step * args.steps / (ms / 1000.0) / 1e6
+    value = aggregate_msps(samples_step, args.steps, world, ms)
     k1_ms = prof.spectral_ms / max(prof.spectral_launches, 1)
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_SAMPLE * samples_step / (k1_ms / 1000.0) / 1e9
@@ -255,7 +279,7 @@ def main():
         steps_e = max(3, min(args.steps, 10))
         ms_e, prof_e, _, _, _ = timed(band_h, host.data_ptr(), steps_e, 3, "e2e")
         e2e = {
-            "value": world * samples_step * steps_e / (ms_e / 1000.0) / 1e6, "unit": "MS/s",
+            "value": aggregate_msps(samples_step, steps_e, world, ms_e), "unit": "MS/s",
             "h2d_bytes_per_step": int(prof_e.h2d_bytes // max(prof_e.pushes, 1)), "d2h_bytes_per_step": int(prof_e.d2h_bytes // max(prof_e.pushes, 1)),
             "steps": steps_e, "ms_per_step": ms_e / steps_e,
         }
@@ -289,7 +313,7 @@ def main():
             "config": {"workload": "configs[1]: single 20 MS/s band, 16384-pt FFT, fused unpack+FFT+power+detect", "fft_size": N_FFT, "sample_rate_hz": SAMPLE_RATE,
                        "frames_per_step": T, "bands_per_gpu": 1, "input": "int8 IQ (CS8)", "l2": "134 MB input per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"bands sharded, {world} GPU(s), no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "k_spectrum<16384>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "k_spectrum<16384>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": K1_DRAM_TRAFFIC_BYTES if T == FRAMES else None, "traffic_source": K1_TRAFFIC_SOURCE,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * samples_step, "kernel_ms": k1_ms,
                          "other_kernels_ms": {"k_detect": prof.detect_ms / max(prof.detect_launches, 1), "k_window_query_total": prof.window_ms / args.steps,
                                               "host_tracker": prof.tracker_host_ms / args.steps}},
