@@ -4,7 +4,9 @@
 Workload (BASELINE.json configs[1], SURVEY.md §8d "Config 2"): ONE 20 MS/s band, N = 16384-point FFT, r = 1,
 T = 4096 frames per step = 67.1 M complex samples = 134 MB of int8 IQ (> the 126 MB L2, so every step streams its
 input from HBM; no L2 flush is needed). A step is one b2s_band_push of T frames: K1 (unpack, window, FFT, dB),
-K2 (noise, Averager, boxcar, threshold, spectrogram) and the host-side signal bookkeeping of the detections.
+K2 (noise, Averager, boxcar, threshold, spectrogram) and the host-side signal bookkeeping of the detections. The band
+runs in its asynchronous result mode (B2S_FLAG_ASYNC): the bookkeeping of step k overlaps the kernels of step k+1, as the
+reference's mailbox does; the timed region ends with b2s_band_sync, i.e. after ALL work of all K steps.
 
   value : steady-state throughput with the IQ already resident in HBM (B2S_FLAG_IQ_ON_DEVICE), CUDA-event timed.
   e2e   : the same call with the IQ in pinned HOST memory: the host->device copy of every step's input and the
@@ -240,6 +242,7 @@ def main():
         for i in range(warmup):
             band.push_raw(ptr, T, int(t_ms), period, res)
             t_ms += T * period
+        band.sync(res)
         band.get_profile(reset=True)
         sampler = ClockSampler(local_rank)
         barrier()
@@ -250,7 +253,8 @@ def main():
         for i in range(steps):
             band.push_raw(ptr, T, int(t_ms), period, res)
             t_ms += T * period
-            last = res.n_transmissions
+        band.sync(res)  # async result mode: every push's kernels AND bookkeeping are complete before the clock stops
+        last = res.n_transmissions
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
@@ -259,7 +263,7 @@ def main():
         return reduce_step_time(ms, dev), prof, clocks, last, res.n_detect_entries
 
     # ---- device-resident run (value + roofline) ----
-    band = make_band(b2s.FLAG_IQ_ON_DEVICE)
+    band = make_band(b2s.FLAG_IQ_ON_DEVICE | b2s.FLAG_ASYNC)
     ms, prof, clocks, n_tx, n_ent = timed(band, iq_dev.data_ptr(), args.steps, args.warmup, "device")
     samples_step = T * N_FFT
     value = aggregate_msps(samples_step, args.steps, world, ms)
@@ -275,7 +279,7 @@ def main():
         host = torch.empty(iq_dev.numel(), dtype=torch.int8, pin_memory=True)
         host.copy_(iq_dev)
         torch.cuda.synchronize()
-        band_h = make_band(0)
+        band_h = make_band(b2s.FLAG_ASYNC)
         steps_e = max(3, min(args.steps, 10))
         ms_e, prof_e, _, _, _ = timed(band_h, host.data_ptr(), steps_e, 3, "e2e")
         e2e = {

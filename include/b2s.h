@@ -50,6 +50,10 @@ extern "C" {
 
 /* b2s_band_config.flags */
 #define B2S_FLAG_IQ_ON_DEVICE 0x100 /* `iq` passed to b2s_band_push is a device pointer */
+#define B2S_FLAG_ASYNC 0x200        /* b2s_band_push returns once the GPU work is enqueued; the signal bookkeeping of push k
+                                       runs on a worker thread while push k+1 is in the kernels (the reference decouples the
+                                       same two halves through its 1-slot mailbox, notification.h:14-26). Results are
+                                       collected with b2s_band_sync; b2s_band_push must be given out = NULL. */
 
 /* Construction-time parameters. The reference takes them from Config / Device / the setupChains lambdas
  * (sdr_device.cpp:148-167, transmission.h:17-25, config.h:24-38). */
@@ -136,6 +140,10 @@ int b2s_band_set_stream(b2s_band* b, void* cuda_stream);
  * iq: n_frames frames, frame k starting at sample k*frame_stride_samples; host memory (pageable or pinned) or,
  * with B2S_FLAG_IQ_ON_DEVICE, device memory. Read-only; may be reused as soon as the call returns. */
 int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, double frame_period_ms, b2s_result* out);
+
+/* Async mode: wait for every outstanding push; `out` (optional) receives the mailbox after the last frame pushed so far
+ * and the statistics accumulated since the previous sync. A no-op returning the last mailbox in synchronous mode. */
+int b2s_band_sync(b2s_band* b, b2s_result* out);
 
 /* ---- profiling (bench.py): per-kernel device time measured with CUDA events on the band's stream ---- */
 typedef struct b2s_profile {

@@ -20,6 +20,7 @@ MAX_IGNORED = 16
 MAX_TX = 64
 IQ_CS8, IQ_CF32 = 0, 1
 FLAG_IQ_ON_DEVICE = 0x100
+FLAG_ASYNC = 0x200
 
 
 class BandConfig(C.Structure):
@@ -180,6 +181,7 @@ def lib():
         L.b2s_band_destroy.argtypes = [C.c_void_p]
         L.b2s_band_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_band_reset.argtypes = [C.c_void_p]
+        L.b2s_band_sync.argtypes = [C.c_void_p, C.POINTER(Result)]
         L.b2s_band_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.b2s_band_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_int]
         L.b2s_band_set_center.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
@@ -331,11 +333,22 @@ class Band:
     def set_stream(self, cuda_stream: int):
         _check(lib().b2s_band_set_stream(self._h, C.c_void_p(cuda_stream)))
 
-    def push_raw(self, iq_ptr: int, n_frames: int, t0_ms: int, frame_period_ms: float, res: Optional[Result] = None) -> Result:
-        """Thin call with a raw pointer (host or device per cfg.flags); used by bench.py."""
+    def push_raw(self, iq_ptr: int, n_frames: int, t0_ms: int, frame_period_ms: float, res: Optional[Result] = None) -> Optional[Result]:
+        """Thin call with a raw pointer (host or device per cfg.flags); used by bench.py. In async mode (FLAG_ASYNC) no
+        result structure is passed; collect with sync()."""
+        if self.cfg.flags & FLAG_ASYNC:
+            _check(lib().b2s_band_push(self._h, C.c_void_p(iq_ptr), n_frames, t0_ms, frame_period_ms, None))
+            return None
         if res is None:
             res = Result()
         _check(lib().b2s_band_push(self._h, C.c_void_p(iq_ptr), n_frames, t0_ms, frame_period_ms, C.byref(res)))
+        return res
+
+    def sync(self, res: Optional[Result] = None) -> Result:
+        """b2s_band_sync: wait for outstanding asynchronous pushes; returns the mailbox after the last frame pushed."""
+        if res is None:
+            res = Result()
+        _check(lib().b2s_band_sync(self._h, C.byref(res)))
         return res
 
     def push(self, iq: np.ndarray, n_frames: int, t0_ms: int, frame_period_ms: float, *, per_frame: bool = False, dense=()) -> PushOutput:

@@ -240,499 +240,7 @@ int validate_config(const b2s_band_config& c) {
 // ------------------------------------------------------------------------------------------------------------
 // band
 // ------------------------------------------------------------------------------------------------------------
-struct NoiseSlot {
-  DevBuf<float> threshold;
-  int samples = 0;
-  bool ready = false;
-};
-struct SpectroSlot {
-  DevBuf<float> sum;
-  int counter = 0;
-  int64_t last_send = 0;
-};
-struct SentRow {
-  int64_t time;
-  int32_t center;
-  std::vector<int8_t> row;
-};
-
-struct b2s_band : public DeviceQueries {
-  b2s_engine* engine = nullptr;
-  b2s_band_config cfg{};
-  std::mutex mutex;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  int max_frames = 0;
-  int slot_capacity = 0;  // detection entries per frame
-
-  SpectralTables tables;
-  DevBuf<unsigned char> d_iq[2];
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_done[2] = {nullptr, nullptr};
-  DevBuf<float> d_psd, d_lin, d_dense_q, d_dense_avg, d_dense_box;
-  DevBuf<int> d_peak_idx;
-  DevBuf<float> d_peak_val;
-  DevBuf<float> d_sum, d_ring[2], d_avg_last, d_ckpt;
-  int ring_cur = 0;  // d_ring[ring_cur] = current ring; the other one = ring as it was before the last push
-  int avg_frames = 0;
-  DevBuf<DetectEntry> d_slots, d_sorted;
-  DevBuf<int> d_slot_count, d_offsets, d_max_count;
-  DevBuf<int> d_spec_slot, d_spec_div;
-  DevBuf<signed char> d_spec_rows;
-  DevBuf<WindowWork> d_work;
-  DevBuf<float> d_wq_val;
-  DevBuf<int> d_wq_idx;
-  PinBuf<DetectEntry> h_entries;
-  PinBuf<int> h_small, h_offsets;
-  PinBuf<WindowWork> h_work;
-
-  std::map<int32_t, NoiseSlot> noise;
-  std::map<int32_t, SpectroSlot> spectro;
-  std::vector<SentRow> sent;
-  int32_t center = 0;
-  Tracker tracker;
-
-  // profiling
-  bool profiling = false;
-  b2s_profile prof{};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-
-  // context of the push being processed (for DeviceQueries)
-  int cur_frames = 0;
-  int cur_noise_samples = 0;
-  std::vector<float> thr_host;
-  bool thr_host_valid = false;
-  std::vector<float> scratch;
-
-  ~b2s_band() {
-    tables.release();
-    d_iq[0].release(); d_iq[1].release(); d_psd.release(); d_lin.release(); d_dense_q.release(); d_dense_avg.release(); d_dense_box.release();
-    d_peak_idx.release(); d_peak_val.release(); d_sum.release(); d_ring[0].release(); d_ring[1].release(); d_avg_last.release();
-    d_ckpt.release(); d_slots.release(); d_sorted.release(); d_slot_count.release(); d_offsets.release(); d_max_count.release(); h_offsets.release(); h_work.release(); d_spec_slot.release(); d_spec_div.release(); d_spec_rows.release();
-    d_work.release(); d_wq_val.release(); d_wq_idx.release(); h_entries.release(); h_small.release();
-    for (auto& kv : noise) kv.second.threshold.release();
-    for (auto& kv : spectro) kv.second.sum.release();
-    for (auto& e : ev) {
-      if (e) cudaEventDestroy(e);
-    }
-    if (copy_stream) cudaStreamDestroy(copy_stream);
-    for (auto& e : copy_done) {
-      if (e) cudaEventDestroy(e);
-    }
-    if (own_stream) cudaStreamDestroy(own_stream);
-  }
-
-  bool learning_frame(int t) const { return cur_noise_samples + t < cfg.learn_frames; }
-
-  int noise_slot(NoiseSlot** out) {
-    auto it = noise.find(center);
-    if (it == noise.end()) {
-      it = noise.emplace(center, NoiseSlot{}).first;
-      int rc = it->second.threshold.alloc(cfg.fft_size);
-      if (rc) return rc;
-      std::vector<float> init(cfg.fft_size, -std::numeric_limits<float>::max());  // noise_learner.cpp:16
-      CU(cudaMemcpyAsync(it->second.threshold.p, init.data(), sizeof(float) * cfg.fft_size, cudaMemcpyHostToDevice, stream));
-      CU(cudaStreamSynchronize(stream));
-    }
-    *out = &it->second;
-    return 0;
-  }
-
-  int ensure_threshold_on_host() {
-    if (thr_host_valid) return 0;
-    NoiseSlot* ns = nullptr;
-    int rc = noise_slot(&ns);
-    if (rc) return rc;
-    thr_host.resize(cfg.fft_size);
-    CU(cudaMemcpyAsync(thr_host.data(), ns->threshold.p, sizeof(float) * cfg.fft_size, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
-    thr_host_valid = true;
-    return 0;
-  }
-
-  // ---- DeviceQueries ----
-  int fetch_ring_window(int frame_first, int rows, int bin_lo, int width, float* out) override {
-    const int n = cfg.fft_size, Y = cfg.grouping_y;
-    int rc = ensure_threshold_on_host();
-    if (rc) return rc;
-    const float* ring_before = d_ring[ring_cur ^ 1].p;  // ring as it was when this push began
-    for (int r = 0; r < rows; ++r) {
-      const int f = frame_first + r;
-      float* dst = out + static_cast<size_t>(r) * width;
-      if (f >= 0) {
-        CU(cudaMemcpyAsync(dst, d_psd.p + static_cast<size_t>(f) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, stream));
-      } else {
-        const int row = Y + f;  // f = -1 is the newest pre-push row
-        if (row < 0) {
-          for (int i = 0; i < width; ++i) dst[i] = 0.0f;  // cannot happen: rows <= Y
-        } else {
-          CU(cudaMemcpyAsync(dst, ring_before + static_cast<size_t>(row) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, stream));
-        }
-      }
-    }
-    CU(cudaStreamSynchronize(stream));
-    for (int r = 0; r < rows; ++r) {
-      const int f = frame_first + r;
-      if (f < 0) continue;
-      float* dst = out + static_cast<size_t>(r) * width;
-      if (learning_frame(f)) {
-        for (int i = 0; i < width; ++i) dst[i] = kNoData;
-      } else {
-        for (int i = 0; i < width; ++i) dst[i] = dst[i] - thr_host[bin_lo + i];  // same IEEE subtraction as the kernel
-      }
-    }
-    return 0;
-  }
-
-  int query_windows(const std::vector<Window>& w, std::vector<std::vector<float>>& values, std::vector<std::vector<int>>& indices) override {
-    std::vector<WindowWork> work;
-    std::vector<int> offset(w.size());
-    int total = 0;
-    int max_width = 0;
-    const int half = cfg.grouping_x / 2;
-    for (size_t q = 0; q < w.size(); ++q) {
-      offset[q] = total;
-      for (int f = w[q].frame_lo; f < w[q].frame_hi;) {
-        const int end = std::min(w[q].frame_hi, (f / kCheckpointEvery + 1) * kCheckpointEvery);
-        work.push_back(WindowWork{w[q].bin_lo, w[q].bin_hi, f, end, total + (f - w[q].frame_lo)});
-        f = end;
-      }
-      total += w[q].frame_hi - w[q].frame_lo;
-      max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half + 2 * kBoxSegment);
-    }
-    // the (small) work list stays in pinned host memory and is read by the kernel through its device alias: a
-    // host->device copy here would queue behind the bulk IQ copy of the next pipeline chunk
-    int rc = h_work.alloc(work.size());
-    if (rc) return rc;
-    if ((rc = d_wq_val.alloc(total))) return rc;
-    if ((rc = d_wq_idx.alloc(total))) return rc;
-    std::memcpy(h_work.p, work.data(), sizeof(WindowWork) * work.size());
-    WindowWork* work_dev = nullptr;
-    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&work_dev), h_work.p, 0));
-    NoiseSlot* ns = nullptr;
-    if ((rc = noise_slot(&ns))) return rc;
-    WindowArgs a{};
-    a.n = cfg.fft_size;
-    a.group_y = cfg.grouping_y;
-    a.group_x = cfg.grouping_x;
-    a.psd = d_psd.p;
-    a.threshold = ns->threshold.p;
-    a.noise_samples = cur_noise_samples;
-    a.learn_frames = cfg.learn_frames;
-    a.ring_in = d_ring[ring_cur ^ 1].p;
-    a.avg_frames = cur_avg_frames_before;
-    a.checkpoints = d_ckpt.p;
-    a.work = work_dev;
-    a.out_value = d_wq_val.p;
-    a.out_index = d_wq_idx.p;
-    const size_t smem = sizeof(float) * 2 * max_width;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_window_query, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    cudaEvent_t w0 = nullptr, w1 = nullptr;
-    if (profiling) {
-      CU(cudaEventCreate(&w0));
-      CU(cudaEventCreate(&w1));
-      CU(cudaEventRecord(w0, stream));
-    }
-    k_window_query<<<static_cast<unsigned>(work.size()), 256, smem, stream>>>(a);
-    CU(cudaGetLastError());
-    if (profiling) CU(cudaEventRecord(w1, stream));
-    prof.window_launches += 1;
-    std::vector<float> v(total);
-    std::vector<int> ix(total);
-    CU(cudaMemcpyAsync(v.data(), d_wq_val.p, sizeof(float) * total, cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemcpyAsync(ix.data(), d_wq_idx.p, sizeof(int) * total, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
-    prof.d2h_bytes += (sizeof(float) + sizeof(int)) * total;
-    if (profiling) {
-      float ms = 0.0f;
-      CU(cudaEventElapsedTime(&ms, w0, w1));
-      prof.window_ms += ms;
-      cudaEventDestroy(w0);
-      cudaEventDestroy(w1);
-    }
-    values.resize(w.size());
-    indices.resize(w.size());
-    for (size_t q = 0; q < w.size(); ++q) {
-      const int len = w[q].frame_hi - w[q].frame_lo;
-      values[q].assign(v.begin() + offset[q], v.begin() + offset[q] + len);
-      indices[q].assign(ix.begin() + offset[q], ix.begin() + offset[q] + len);
-    }
-    return 0;
-  }
-  int cur_avg_frames_before = 0;
-
-  int init(b2s_engine* e, const b2s_band_config& c) {
-    engine = e;
-    cfg = c;
-    CU(cudaSetDevice(e->device));
-    max_frames = c.max_frames_per_push > 0 ? c.max_frames_per_push : 4096;
-    slot_capacity = c.detect_capacity > 0 ? c.detect_capacity : 256;
-    center = c.center_hz;
-    CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
-    stream = own_stream;
-    int rc = tables.build(c);
-    if (rc) return rc;
-    cfg.window_taps = nullptr;
-    const size_t n = c.fft_size, Y = c.grouping_y;
-    if ((rc = d_psd.alloc(static_cast<size_t>(max_frames) * n))) return rc;
-    if ((rc = d_peak_idx.alloc(max_frames))) return rc;
-    if ((rc = d_peak_val.alloc(max_frames))) return rc;
-    if ((rc = d_sum.alloc(n))) return rc;
-    if ((rc = d_ring[0].alloc(Y * n))) return rc;
-    if ((rc = d_ring[1].alloc(Y * n))) return rc;
-    if ((rc = d_avg_last.alloc(n))) return rc;
-    if ((rc = d_ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
-    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
-    if ((rc = d_sorted.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
-    if ((rc = d_slot_count.alloc(max_frames))) return rc;
-    if ((rc = d_offsets.alloc(max_frames + 1))) return rc;
-    if ((rc = d_max_count.alloc(1))) return rc;
-    if ((rc = h_offsets.alloc(max_frames + 2))) return rc;
-    if ((rc = d_spec_slot.alloc(max_frames))) return rc;
-    if ((rc = h_small.alloc(max_frames + 64))) return rc;
-    if ((rc = h_entries.alloc(static_cast<size_t>(max_frames) * 64))) return rc;
-    rc = reset_averager();
-    if (rc) return rc;
-    // tracker parameters
-    TrackerParams& p = tracker.p;
-    p.n = c.fft_size;
-    p.sample_rate = c.sample_rate_hz;
-    p.center = c.center_hz;
-    p.range_lo = c.range_lo_hz;
-    p.range_hi = c.range_hi_hz;
-    p.n_ignored = c.n_ignored;
-    for (int i = 0; i < c.n_ignored; ++i) {
-      p.ignored_lo[i] = c.ignored_lo_hz[i];
-      p.ignored_hi[i] = c.ignored_hi_hz[i];
-    }
-    p.group_size = c.group_size_bins;
-    p.group_y = c.grouping_y;
-    p.start_level = c.start_level;
-    p.stop_level = c.stop_level;
-    p.tuning_step = c.tuning_step_hz;
-    p.min_time = c.min_time_ms;
-    p.timeout = c.timeout_ms;
-    p.max_time = c.max_time_ms;
-    return 0;
-  }
-
-  // Averager::reset (averager.cpp:27-34) / constructor state (averager.cpp:7-12)
-  int reset_averager() {
-    const size_t n = cfg.fft_size, Y = cfg.grouping_y;
-    CU(cudaMemsetAsync(d_sum.p, 0, sizeof(float) * n, stream));
-    CU(cudaMemsetAsync(d_ring[0].p, 0, sizeof(float) * Y * n, stream));
-    CU(cudaMemsetAsync(d_ring[1].p, 0, sizeof(float) * Y * n, stream));
-    std::vector<float> nd(n, kNoData);
-    CU(cudaMemcpyAsync(d_avg_last.p, nd.data(), sizeof(float) * n, cudaMemcpyHostToDevice, stream));
-    CU(cudaStreamSynchronize(stream));
-    avg_frames = 0;
-    ring_cur = 0;
-    return 0;
-  }
-
-  int push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out);
-};
-
-int b2s_band::push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
-  const int n = cfg.fft_size, Y = cfg.grouping_y;
-  const int T = static_cast<int>(frames);
-  const size_t bytes_per_sample = cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
-  const bool want_dense_q = out && out->noise_sub_db, want_dense_avg = out && out->avg_db, want_dense_box = out && out->box_db;
-  int rc;
-  if (want_dense_q && (rc = d_dense_q.alloc(static_cast<size_t>(max_frames) * n))) return rc;
-  if (want_dense_avg && (rc = d_dense_avg.alloc(static_cast<size_t>(max_frames) * n))) return rc;
-  if (want_dense_box && (rc = d_dense_box.alloc(static_cast<size_t>(max_frames) * n))) return rc;
-
-  // ---- K1: spectra ----
-  SpectralArgs sa{};
-  sa.iq = iq_dev;
-  sa.frame_stride_bytes = static_cast<long long>(cfg.frame_stride_samples) * bytes_per_sample;
-  sa.n_frames = T;
-  sa.wscale = tables.wscale.p;
-  sa.twiddle = tables.twiddle.p;
-  sa.inv_fs = 1.0f / static_cast<float>(cfg.sample_rate_hz);
-  sa.psd_db = d_psd.p;
-  sa.power_lin = nullptr;
-  sa.peak_index = d_peak_idx.p;
-  sa.peak_value = d_peak_val.p;
-  if (profiling) CU(cudaEventRecord(ev[0], stream));
-  if ((rc = launch_spectrum(engine, n, cfg.iq_format, sa, stream))) return rc;
-  if (profiling) CU(cudaEventRecord(ev[1], stream));
-
-  // ---- plan the spectrogram emissions of this chunk from the clock (Spectrogram::send, spectrogram.cpp:62-75) ----
-  int n_slots = 0;
-  int emit_frames[kMaxSpecEmits] = {0}, emit_divs[kMaxSpecEmits] = {0};
-  SpectroSlot* ss = nullptr;
-  const int M = cfg.spectrogram_out_size;
-  std::vector<int64_t> slot_time;
-  if (M > 0) {
-    auto it = spectro.find(center);
-    if (it == spectro.end()) {
-      it = spectro.emplace(center, SpectroSlot{}).first;
-      if ((rc = it->second.sum.alloc(M))) return rc;
-      CU(cudaMemsetAsync(it->second.sum.p, 0, sizeof(float) * M, stream));
-      it->second.counter = 0;  // the reference leaves m_counter uninitialised (spectrogram.cpp:9); defined as 0
-      it->second.last_send = host::frame_time(t0_ms, period_ms, frame_offset);  // Container ctor: getTime()
-    }
-    ss = &it->second;
-    for (int t = 0; t < T; ++t) {
-      const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
-      ss->counter++;
-      if (ss->last_send + cfg.spectrogram_interval_ms < now) {
-        if (n_slots >= kMaxSpecEmits) return fail(B2S_E_INVALID, "more than %d spectrogram rows fall into one push chunk; push fewer frames or raise the interval", kMaxSpecEmits);
-        emit_frames[n_slots] = t;
-        emit_divs[n_slots] = ss->counter;
-        ++n_slots;
-        slot_time.push_back(now);
-        ss->counter = 0;
-        ss->last_send = now;
-      }
-    }
-    if (n_slots > 0 && (rc = d_spec_rows.alloc(static_cast<size_t>(n_slots) * M))) return rc;
-  }
-
-  // ---- K2: noise / averager / boxcar / detect / spectrogram ----
-  NoiseSlot* ns = nullptr;
-  if ((rc = noise_slot(&ns))) return rc;
-  CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
-  CU(cudaMemsetAsync(d_max_count.p, 0, sizeof(int), stream));
-  DetectArgs da{};
-  da.n = n;
-  da.n_frames = T;
-  da.group_y = Y;
-  da.group_x = cfg.grouping_x;
-  da.psd = d_psd.p;
-  da.threshold = ns->threshold.p;
-  da.noise_samples = ns->ready ? cfg.learn_frames : ns->samples;
-  da.learn_frames = cfg.learn_frames;
-  da.avg_sum = d_sum.p;
-  da.ring_in = d_ring[ring_cur].p;
-  da.ring_out = d_ring[ring_cur ^ 1].p;
-  da.avg_frames = avg_frames;
-  da.avg_last = d_avg_last.p;
-  da.checkpoints = d_ckpt.p;
-  da.detect_level = std::min(cfg.start_level, cfg.stop_level);
-  da.slots = d_slots.p;
-  da.slot_count = d_slot_count.p;
-  da.slot_capacity = slot_capacity;
-  da.spec_out = M;
-  da.spec_sum = ss ? ss->sum.p : nullptr;
-  da.n_emit = n_slots;
-  for (int i = 0; i < n_slots; ++i) {
-    da.emit_frame[i] = emit_frames[i];
-    da.emit_div[i] = emit_divs[i];
-  }
-  da.spec_rows = d_spec_rows.p;
-  da.dense_q = want_dense_q ? d_dense_q.p : nullptr;
-  da.dense_avg = want_dense_avg ? d_dense_avg.p : nullptr;
-  da.dense_box = want_dense_box ? d_dense_box.p : nullptr;
-  {
-    const int half = cfg.grouping_x / 2;
-    const int hp = (half + 3) & ~3;
-    const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * 3 * kDetectTileFrames +
-                        sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta;
-    const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
-    static bool configured = false;
-    if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-    if (profiling) CU(cudaEventRecord(ev[2], stream));
-    if (half == 10 && Y == 21) {
-      k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da);
-    } else {
-      k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da);
-    }
-    CU(cudaGetLastError());
-    // order the per-frame slot lists by bin into one dense array
-    k_entries_prefix<<<1, 1024, 0, stream>>>(d_slot_count.p, slot_capacity, T, d_offsets.p, d_max_count.p);
-    CU(cudaGetLastError());
-    k_entries_sort<<<(T * 32 + 255) / 256, 256, 0, stream>>>(d_slots.p, d_slot_count.p, slot_capacity, T, d_offsets.p, d_sorted.p);
-    CU(cudaGetLastError());
-    if (profiling) CU(cudaEventRecord(ev[3], stream));
-  }
-  // push context for the tracker's device queries
-  cur_frames = T;
-  cur_noise_samples = da.noise_samples;
-  cur_avg_frames_before = avg_frames;
-  thr_host_valid = false;
-  // host mirrors of the scalar state
-  if (!ns->ready) {
-    ns->samples = std::min(ns->samples + T, cfg.learn_frames);
-    ns->ready = ns->samples >= cfg.learn_frames;
-  }
-  avg_frames = std::min(avg_frames + T, Y);
-  ring_cur ^= 1;
-
-  // ---- results: detection entries -> tracker ----
-  int* h_off = h_offsets.p;
-  int* h_max = h_small.p + max_frames;
-  CU(cudaMemcpyAsync(h_off, d_offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, stream));
-  CU(cudaMemcpyAsync(h_max, d_max_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  CU(cudaStreamSynchronize(stream));
-  const int n_entries = h_off[T];
-  prof.frames += T;
-  prof.spectral_launches += 1;
-  prof.detect_launches += 1;  // k_detect (+ the two small list-ordering kernels, timed with it)
-  prof.d2h_bytes += sizeof(int) * (T + 2);
-  if (profiling) {
-    float ms = 0.0f;
-    CU(cudaEventElapsedTime(&ms, ev[0], ev[1]));
-    prof.spectral_ms += ms;
-    CU(cudaEventElapsedTime(&ms, ev[2], ev[3]));
-    prof.detect_ms += ms;
-  }
-  const auto host_t0 = std::chrono::steady_clock::now();
-  if (*h_max > slot_capacity) return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries; detect_capacity is %d per frame", *h_max, slot_capacity);
-  if (n_entries > 0) {
-    if ((rc = h_entries.alloc(n_entries))) return rc;
-    CU(cudaMemcpyAsync(h_entries.p, d_sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
-    prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
-  }
-  const bool every = out && out->frame_tx_count;
-  std::vector<Tracker::FrameState> states;
-  rc = tracker.run(h_entries.p, h_off, frames, t0_ms, period_ms, frame_offset, *this, every, states);
-  if (rc) return rc;
-  prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-
-  // ---- copy-out ----
-  if (out) {
-    out->n_detect_entries += n_entries;
-    out->n_spectrogram_rows += n_slots;
-    if (every) {
-      for (int t = 0; t < T; ++t) out->frame_tx_count[frame_offset + t] = 0;
-      for (const auto& fs : states) {
-        out->frame_tx_count[frame_offset + fs.frame] =
-            tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
-      }
-    }
-    // the mailbox after the last frame of this chunk
-    out->n_transmissions = 0;
-    if (!states.empty() && states.back().frame == T - 1) {
-      const int total = tracker.sorted_transmissions(states.back(), out->transmissions, B2S_MAX_TX);
-      out->n_transmissions = std::min(total, B2S_MAX_TX);
-    }
-    if (out->peak_index) CU(cudaMemcpyAsync(out->peak_index + frame_offset, d_peak_idx.p, sizeof(int) * T, cudaMemcpyDeviceToHost, stream));
-    if (out->peak_value) CU(cudaMemcpyAsync(out->peak_value + frame_offset, d_peak_val.p, sizeof(float) * T, cudaMemcpyDeviceToHost, stream));
-    const size_t row_bytes = sizeof(float) * static_cast<size_t>(T) * n, off = frame_offset * n;
-    if (out->psd_db) CU(cudaMemcpyAsync(out->psd_db + off, d_psd.p, row_bytes, cudaMemcpyDeviceToHost, stream));
-    if (out->noise_sub_db) CU(cudaMemcpyAsync(out->noise_sub_db + off, d_dense_q.p, row_bytes, cudaMemcpyDeviceToHost, stream));
-    if (out->avg_db) CU(cudaMemcpyAsync(out->avg_db + off, d_dense_avg.p, row_bytes, cudaMemcpyDeviceToHost, stream));
-    if (out->box_db) CU(cudaMemcpyAsync(out->box_db + off, d_dense_box.p, row_bytes, cudaMemcpyDeviceToHost, stream));
-  }
-  if (n_slots > 0) {
-    std::vector<int8_t> rows(static_cast<size_t>(n_slots) * M);
-    CU(cudaMemcpyAsync(rows.data(), d_spec_rows.p, rows.size(), cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
-    for (int s = 0; s < n_slots; ++s) {
-      sent.push_back(SentRow{slot_time[s], center, std::vector<int8_t>(rows.begin() + static_cast<size_t>(s) * M, rows.begin() + static_cast<size_t>(s + 1) * M)});
-    }
-  }
-  CU(cudaStreamSynchronize(stream));
-  return 0;
-}
+#include "band.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
 // stand-alone device Averager
@@ -850,6 +358,8 @@ int b2s_band_destroy(b2s_band* b) {
 int b2s_band_set_stream(b2s_band* b, void* cuda_stream) {
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
   b->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->own_stream;
   return 0;
 }
@@ -858,6 +368,7 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
   if (!b || (!iq && n_frames)) return fail(B2S_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
+  if (b->async_mode && out) return fail(B2S_E_INVALID, "with B2S_FLAG_ASYNC results are collected by b2s_band_sync; pass out = NULL to b2s_band_push");
   if (out) {
     out->n_transmissions = 0;
     out->n_detect_entries = 0;
@@ -878,7 +389,9 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
   }
   // Host input: the push is cut into pipeline chunks; the host->device copy of chunk i+1 runs on a second stream
   // while chunk i is in the kernels / tracker (double-buffered staging), so PCIe time hides behind compute (or vice versa).
-  const size_t pipe = std::max<size_t>(1, std::min<size_t>(b->max_frames, n_frames >= 512 ? (n_frames + 3) / 4 : n_frames));
+  // In async mode one chunk per push is enough: the copy of push k+1 already overlaps the work of push k.
+  const size_t pipe = b->async_mode ? std::min<size_t>(b->max_frames, std::max<size_t>(n_frames, 1))
+                                    : std::max<size_t>(1, std::min<size_t>(b->max_frames, n_frames >= 512 ? (n_frames + 3) / 4 : n_frames));
   if (!b->copy_stream) {
     CU(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&b->copy_done[0], cudaEventDisableTiming));
@@ -898,48 +411,59 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
     b->prof.h2d_bytes += bytes;
     return 0;
   };
-  int slot = 0;
-  const bool trace = getenv("B2S_TRACE") != nullptr;
-  cudaEvent_t tr[32];
-  int ntr = 0;
-  auto mark = [&](cudaStream_t st) {
-    if (trace && ntr < 32) {
-      cudaEventCreate(&tr[ntr]);
-      cudaEventRecord(tr[ntr], st);
-      ++ntr;
+  if (b->async_mode) {
+    // staging buffer iq_slot was last read by the K1 of the chunk two chunks ago; iq_prev_use[slot] marks the end of that
+    // chunk's kernels on b->stream, and the copy stream waits for it before overwriting the buffer
+    for (size_t done = 0; done < n_frames;) {
+      const size_t chunk = chunk_len(done);
+      const int slot = b->iq_slot;
+      CU(cudaStreamWaitEvent(b->copy_stream, b->iq_prev_use[slot], 0));
+      int rc = start_copy(done, slot);
+      if (rc) return rc;
+      CU(cudaStreamWaitEvent(b->stream, b->copy_done[slot], 0));
+      rc = b->push_chunk(b->d_iq[slot].p, chunk, t0_ms, frame_period_ms, done, nullptr);
+      if (rc) return rc;
+      CU(cudaEventRecord(b->iq_prev_use[slot], b->stream));  // K1 (and the rest) of this chunk: the buffer may be overwritten after it
+      CU(cudaStreamSynchronize(b->copy_stream));             // the caller may reuse `iq` as soon as the call returns
+      b->iq_slot ^= 1;
+      done += chunk;
     }
-  };
+    return 0;
+  }
+  int slot = 0;
   if (n_frames > 0) {
-    mark(b->copy_stream);
     int rc = start_copy(0, 0);
     if (rc) return rc;
-    mark(b->copy_stream);
   }
   for (size_t done = 0; done < n_frames;) {
     const size_t chunk = chunk_len(done);
     CU(cudaStreamWaitEvent(b->stream, b->copy_done[slot], 0));
     if (done + chunk < n_frames) {  // the other staging buffer was released when the previous chunk finished (push_chunk is synchronous)
-      mark(b->copy_stream);
       int rc = start_copy(done + chunk, slot ^ 1);
       if (rc) return rc;
-      mark(b->copy_stream);
     }
-    mark(b->stream);
     int rc = b->push_chunk(b->d_iq[slot].p, chunk, t0_ms, frame_period_ms, done, out);
     if (rc) return rc;
-    mark(b->stream);
     done += chunk;
     slot ^= 1;
   }
-  if (trace) {
-    cudaDeviceSynchronize();
-    for (int i = 1; i < ntr; ++i) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, tr[0], tr[i]);
-      fprintf(stderr, "trace[%d] %.3f ms\n", i, ms);
-    }
-    for (int i = 0; i < ntr; ++i) cudaEventDestroy(tr[i]);
+  return 0;
+}
+
+int b2s_band_sync(b2s_band* b, b2s_result* out) {
+  if (!b) return fail(B2S_E_INVALID, "NULL band");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
+  int rc = b->drain();
+  if (rc) return rc;
+  if (out) {
+    out->n_transmissions = b->mailbox_count;
+    std::memcpy(out->transmissions, b->mailbox, sizeof(b2s_transmission) * b->mailbox_count);
+    out->n_detect_entries = b->stat_entries;
+    out->n_spectrogram_rows = b->stat_rows;
   }
+  b->stat_entries = 0;
+  b->stat_rows = 0;
   return 0;
 }
 
@@ -947,17 +471,16 @@ int b2s_band_set_profiling(b2s_band* b, int enable) {
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
-  if (enable) {
-    for (auto& e : b->ev) {
-      if (!e) CU(cudaEventCreate(&e));
-    }
-  }
+  int rc = b->drain();
+  if (rc) return rc;
   b->profiling = enable != 0;
   return 0;
 }
 int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset) {
   if (!b || !out) return fail(B2S_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
   *out = b->prof;
   if (reset) b->prof = b2s_profile{};
   return 0;
@@ -967,6 +490,9 @@ int b2s_band_reset(b2s_band* b) {
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
+  int rc = b->drain();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(b->stream));
   b->tracker.reset();
   return b->reset_averager();
 }
@@ -974,6 +500,8 @@ int b2s_band_reset(b2s_band* b) {
 int b2s_band_set_center(b2s_band* b, int32_t center_hz, int32_t lo, int32_t hi) {
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
   b->center = center_hz;
   b->tracker.p.center = center_hz;
   b->tracker.p.range_lo = lo;
@@ -985,6 +513,9 @@ int b2s_band_get_averager(b2s_band* b, float* sum, float* avg, float* ring, int3
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
+  int rc = b->drain();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(b->stream));
   const size_t n = b->cfg.fft_size, Y = b->cfg.grouping_y;
   if (sum) CU(cudaMemcpy(sum, b->d_sum.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
   if (avg) CU(cudaMemcpy(avg, b->d_avg_last.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
@@ -997,6 +528,9 @@ int b2s_band_get_noise(b2s_band* b, float* threshold, int32_t* samples, int32_t*
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
+  int rc = b->drain();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(b->stream));
   auto it = b->noise.find(b->center);
   if (it == b->noise.end()) {
     if (samples) *samples = 0;
@@ -1015,6 +549,8 @@ int b2s_band_get_noise(b2s_band* b, float* threshold, int32_t* samples, int32_t*
 int b2s_band_get_spectrogram(b2s_band* b, int64_t* times, int32_t* centers, int8_t* rows, int cap, int consume, int* count) {
   if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
   const int M = b->cfg.spectrogram_out_size;
   const int total = static_cast<int>(b->sent.size());
   for (int i = 0; i < total && i < cap; ++i) {
@@ -1030,6 +566,8 @@ int b2s_band_get_spectrogram(b2s_band* b, int64_t* times, int32_t* centers, int8
 int b2s_band_get_signals(b2s_band* b, int32_t* keys, int64_t* first, int64_t* last, float* power, int cap, int* count) {
   if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
   int i = 0;
   for (const auto& kv : b->tracker.signals) {
     if (i < cap) {

@@ -1,0 +1,658 @@
+// b2s_band: per-band state, the two halves of a push (GPU enqueue / result finish) and the optional result worker.
+// Included by b2s_api.cu after its helpers (fail, CU, DevBuf, PinBuf, launch_spectrum, SpectralTables).
+//
+// A push (or each pipeline chunk of one) goes through
+//   enqueue_chunk : K1 -> K2 -> entry ordering on the band's stream, non-blocking on the host
+//   finish_chunk  : read back the ordered detection entries, run the signal bookkeeping (tracker.h, K3 on demand),
+//                   collect spectrogram rows / requested dense rows
+// In the default (synchronous) mode both run on the caller's thread, one after the other. With B2S_FLAG_ASYNC the finish
+// half runs on a worker thread with its own stream and a second set of per-push buffers ("slots"), so the kernels of
+// push k+1 overlap the bookkeeping of push k — the same decoupling the reference gets from its 1-slot mailbox between
+// the Transmission block thread and the Scanner thread (transmission.cpp:67, notification.h:14-26).
+#pragma once
+
+#include <condition_variable>
+#include <deque>
+#include <thread>
+
+struct NoiseSlot {
+  DevBuf<float> threshold;
+  int samples = 0;
+  bool ready = false;
+};
+struct SpectroSlot {
+  DevBuf<float> sum;
+  int counter = 0;
+  int64_t last_send = 0;
+};
+struct SentRow {
+  int64_t time;
+  int32_t center;
+  std::vector<int8_t> row;
+};
+
+constexpr int kPushSlots = 2;
+constexpr int kRings = 3;  // ring before push k must survive while push k+1 writes its own "after" ring
+
+struct PushSlot {
+  // device buffers owned by the slot (live until the slot's finish half is done)
+  DevBuf<float> psd, ckpt, dense_q, dense_avg, dense_box, peak_val;
+  DevBuf<int> peak_idx, offsets, max_count;
+  DevBuf<DetectEntry> sorted;
+  DevBuf<signed char> spec_rows;
+  PinBuf<int> h_offsets;
+  PinBuf<DetectEntry> h_entries;
+  cudaEvent_t gpu_done = nullptr, ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // context of the chunk in flight
+  bool busy = false;
+  int T = 0;
+  int64_t t0_ms = 0;
+  double period_ms = 0.0;
+  size_t frame_offset = 0;
+  int noise_samples = 0, avg_frames_before = 0, ring_before = 0;
+  const float* threshold = nullptr;
+  int32_t center = 0;
+  int n_emit = 0;
+  std::vector<int64_t> emit_time;
+  bool dense_q_on = false, dense_avg_on = false, dense_box_on = false;
+  b2s_result* out = nullptr;  // synchronous mode only
+  std::vector<float> thr_host;
+  bool thr_host_valid = false;
+  void release() {
+    psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
+    peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
+    h_offsets.release(); h_entries.release();
+    if (gpu_done) cudaEventDestroy(gpu_done);
+    for (auto& e : ev) {
+      if (e) cudaEventDestroy(e);
+    }
+  }
+};
+
+struct b2s_band : public DeviceQueries {
+  b2s_engine* engine = nullptr;
+  b2s_band_config cfg{};
+  std::mutex mutex;  // serialises API calls on this band
+  cudaStream_t own_stream = nullptr, stream = nullptr, finish_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr}, iq_prev_use[2] = {nullptr, nullptr};
+  int iq_slot = 0;
+  int max_frames = 0;
+  int slot_capacity = 0;  // detection entries per frame
+  bool async_mode = false;
+
+  SpectralTables tables;
+  DevBuf<unsigned char> d_iq[2];
+  DevBuf<float> d_sum, d_ring[kRings], d_avg_last;
+  int ring_cur = 0;  // d_ring[ring_cur] = ring after the last enqueued push
+  int avg_frames = 0;
+  DevBuf<DetectEntry> d_slots;
+  DevBuf<int> d_slot_count;
+  DevBuf<float> d_wq_val;
+  DevBuf<int> d_wq_idx;
+  PinBuf<WindowWork> h_work;
+  PushSlot slots[kPushSlots];
+  int next_slot = 0;
+
+  std::map<int32_t, NoiseSlot> noise;
+  std::map<int32_t, SpectroSlot> spectro;
+  std::vector<SentRow> sent;
+  int32_t center = 0;
+  Tracker tracker;
+
+  // result of the most recently finished chunk (the mailbox) + statistics since the last sync
+  b2s_transmission mailbox[B2S_MAX_TX];
+  int mailbox_count = 0;
+  int stat_entries = 0, stat_rows = 0;
+
+  // profiling
+  bool profiling = false;
+  b2s_profile prof{};
+
+  // worker (async mode)
+  std::thread worker;
+  std::mutex qmutex;
+  std::condition_variable qcv;
+  std::deque<int> queue;
+  bool stop_worker = false;
+  int worker_rc = 0;
+  std::string worker_error;
+
+  PushSlot* cur = nullptr;  // slot whose finish half is running (DeviceQueries context)
+  cudaStream_t fstream() const { return async_mode ? finish_stream : stream; }
+
+  ~b2s_band() {
+    shutdown_worker();
+    tables.release();
+    d_iq[0].release(); d_iq[1].release(); d_sum.release(); d_avg_last.release();
+    for (auto& r : d_ring) r.release();
+    d_slots.release(); d_slot_count.release(); d_wq_val.release(); d_wq_idx.release(); h_work.release();
+    for (auto& s : slots) s.release();
+    for (auto& kv : noise) kv.second.threshold.release();
+    for (auto& kv : spectro) kv.second.sum.release();
+    for (auto& e : copy_done) {
+      if (e) cudaEventDestroy(e);
+    }
+    for (auto& e : iq_prev_use) {
+      if (e) cudaEventDestroy(e);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (finish_stream) cudaStreamDestroy(finish_stream);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  // ---------------------------------------------------------------------------------------------------------
+  int noise_slot(NoiseSlot** out) {
+    auto it = noise.find(center);
+    if (it == noise.end()) {
+      it = noise.emplace(center, NoiseSlot{}).first;
+      int rc = it->second.threshold.alloc(cfg.fft_size);
+      if (rc) return rc;
+      std::vector<float> init(cfg.fft_size, -std::numeric_limits<float>::max());  // noise_learner.cpp:16
+      CU(cudaMemcpyAsync(it->second.threshold.p, init.data(), sizeof(float) * cfg.fft_size, cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+    }
+    *out = &it->second;
+    return 0;
+  }
+
+  // ---- DeviceQueries (called from the tracker during the finish half; read the slot's buffers) ----
+  int fetch_ring_window(int frame_first, int rows, int bin_lo, int width, float* out) override {
+    PushSlot& s = *cur;
+    const int n = cfg.fft_size, Y = cfg.grouping_y;
+    cudaStream_t st = fstream();
+    if (!s.thr_host_valid) {
+      s.thr_host.resize(n);
+      CU(cudaMemcpyAsync(s.thr_host.data(), s.threshold, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      s.thr_host_valid = true;
+    }
+    const float* ring_before = d_ring[s.ring_before].p;  // ring as it was when this push began
+    for (int r = 0; r < rows; ++r) {
+      const int f = frame_first + r;
+      float* dst = out + static_cast<size_t>(r) * width;
+      if (f >= 0) {
+        CU(cudaMemcpyAsync(dst, s.psd.p + static_cast<size_t>(f) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, st));
+      } else if (Y + f >= 0) {  // f = -1 is the newest pre-push row
+        CU(cudaMemcpyAsync(dst, ring_before + static_cast<size_t>(Y + f) * n + bin_lo, sizeof(float) * width, cudaMemcpyDeviceToHost, st));
+      } else {
+        for (int i = 0; i < width; ++i) dst[i] = 0.0f;
+      }
+    }
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < rows; ++r) {
+      const int f = frame_first + r;
+      if (f < 0) continue;
+      float* dst = out + static_cast<size_t>(r) * width;
+      if (s.noise_samples + f < cfg.learn_frames) {
+        for (int i = 0; i < width; ++i) dst[i] = kNoData;
+      } else {
+        for (int i = 0; i < width; ++i) dst[i] = dst[i] - s.thr_host[bin_lo + i];  // same IEEE subtraction as the kernel
+      }
+    }
+    return 0;
+  }
+
+  int query_windows(const std::vector<Window>& w, std::vector<std::vector<float>>& values, std::vector<std::vector<int>>& indices) override {
+    PushSlot& s = *cur;
+    cudaStream_t st = fstream();
+    std::vector<WindowWork> work;
+    std::vector<int> offset(w.size());
+    int total = 0, max_width = 0;
+    const int half = cfg.grouping_x / 2;
+    for (size_t q = 0; q < w.size(); ++q) {
+      offset[q] = total;
+      for (int f = w[q].frame_lo; f < w[q].frame_hi;) {
+        const int end = std::min(w[q].frame_hi, (f / kCheckpointEvery + 1) * kCheckpointEvery);
+        work.push_back(WindowWork{w[q].bin_lo, w[q].bin_hi, f, end, total + (f - w[q].frame_lo)});
+        f = end;
+      }
+      total += w[q].frame_hi - w[q].frame_lo;
+      max_width = std::max(max_width, w[q].bin_hi - w[q].bin_lo + 1 + 2 * half + 2 * kBoxSegment);
+    }
+    // the (small) work list stays in pinned host memory and is read by the kernel through its device alias: a
+    // host->device copy here would queue behind the bulk IQ copy of the next pipeline chunk
+    int rc = h_work.alloc(work.size());
+    if (rc) return rc;
+    if ((rc = d_wq_val.alloc(total))) return rc;
+    if ((rc = d_wq_idx.alloc(total))) return rc;
+    std::memcpy(h_work.p, work.data(), sizeof(WindowWork) * work.size());
+    WindowWork* work_dev = nullptr;
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&work_dev), h_work.p, 0));
+    WindowArgs a{};
+    a.n = cfg.fft_size;
+    a.group_y = cfg.grouping_y;
+    a.group_x = cfg.grouping_x;
+    a.psd = s.psd.p;
+    a.threshold = s.threshold;
+    a.noise_samples = s.noise_samples;
+    a.learn_frames = cfg.learn_frames;
+    a.ring_in = d_ring[s.ring_before].p;
+    a.avg_frames = s.avg_frames_before;
+    a.checkpoints = s.ckpt.p;
+    a.work = work_dev;
+    a.out_value = d_wq_val.p;
+    a.out_index = d_wq_idx.p;
+    const size_t smem = sizeof(float) * 2 * max_width;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_window_query, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaEvent_t w0 = nullptr, w1 = nullptr;
+    if (profiling) {
+      CU(cudaEventCreate(&w0));
+      CU(cudaEventCreate(&w1));
+      CU(cudaEventRecord(w0, st));
+    }
+    k_window_query<<<static_cast<unsigned>(work.size()), 256, smem, st>>>(a);
+    CU(cudaGetLastError());
+    if (profiling) CU(cudaEventRecord(w1, st));
+    prof.window_launches += 1;
+    std::vector<float> v(total);
+    std::vector<int> ix(total);
+    CU(cudaMemcpyAsync(v.data(), d_wq_val.p, sizeof(float) * total, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ix.data(), d_wq_idx.p, sizeof(int) * total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    prof.d2h_bytes += (sizeof(float) + sizeof(int)) * total;
+    if (profiling) {
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, w0, w1));
+      prof.window_ms += ms;
+      cudaEventDestroy(w0);
+      cudaEventDestroy(w1);
+    }
+    values.resize(w.size());
+    indices.resize(w.size());
+    for (size_t q = 0; q < w.size(); ++q) {
+      const int len = w[q].frame_hi - w[q].frame_lo;
+      values[q].assign(v.begin() + offset[q], v.begin() + offset[q] + len);
+      indices[q].assign(ix.begin() + offset[q], ix.begin() + offset[q] + len);
+    }
+    return 0;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------
+  int init(b2s_engine* e, const b2s_band_config& c) {
+    engine = e;
+    cfg = c;
+    CU(cudaSetDevice(e->device));
+    max_frames = c.max_frames_per_push > 0 ? c.max_frames_per_push : 4096;
+    slot_capacity = c.detect_capacity > 0 ? c.detect_capacity : 256;
+    async_mode = (c.flags & B2S_FLAG_ASYNC) != 0;
+    center = c.center_hz;
+    CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&finish_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+    int rc = tables.build(c);
+    if (rc) return rc;
+    cfg.window_taps = nullptr;
+    const size_t n = c.fft_size, Y = c.grouping_y;
+    const int n_slots = async_mode ? kPushSlots : 1;
+    for (int i = 0; i < n_slots; ++i) {
+      PushSlot& s = slots[i];
+      if ((rc = s.psd.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+      if ((rc = s.peak_idx.alloc(max_frames))) return rc;
+      if ((rc = s.peak_val.alloc(max_frames))) return rc;
+      if ((rc = s.ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
+      if ((rc = s.sorted.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
+      if ((rc = s.offsets.alloc(max_frames + 1))) return rc;
+      if ((rc = s.max_count.alloc(1))) return rc;
+      if ((rc = s.h_offsets.alloc(max_frames + 2))) return rc;
+      if ((rc = s.h_entries.alloc(static_cast<size_t>(max_frames) * 64))) return rc;
+      CU(cudaEventCreateWithFlags(&s.gpu_done, cudaEventDisableTiming));
+    }
+    if ((rc = d_sum.alloc(n))) return rc;
+    for (auto& r : d_ring) {
+      if ((rc = r.alloc(Y * n))) return rc;
+    }
+    if ((rc = d_avg_last.alloc(n))) return rc;
+    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
+    if ((rc = d_slot_count.alloc(max_frames))) return rc;
+    rc = reset_averager();
+    if (rc) return rc;
+    TrackerParams& p = tracker.p;
+    p.n = c.fft_size;
+    p.sample_rate = c.sample_rate_hz;
+    p.center = c.center_hz;
+    p.range_lo = c.range_lo_hz;
+    p.range_hi = c.range_hi_hz;
+    p.n_ignored = c.n_ignored;
+    for (int i = 0; i < c.n_ignored; ++i) {
+      p.ignored_lo[i] = c.ignored_lo_hz[i];
+      p.ignored_hi[i] = c.ignored_hi_hz[i];
+    }
+    p.group_size = c.group_size_bins;
+    p.group_y = c.grouping_y;
+    p.start_level = c.start_level;
+    p.stop_level = c.stop_level;
+    p.tuning_step = c.tuning_step_hz;
+    p.min_time = c.min_time_ms;
+    p.timeout = c.timeout_ms;
+    p.max_time = c.max_time_ms;
+    if (async_mode) {
+      for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&iq_prev_use[i], cudaEventDisableTiming));
+        CU(cudaEventRecord(iq_prev_use[i], stream));
+      }
+      worker = std::thread([this]() { worker_loop(); });
+    }
+    return 0;
+  }
+
+  // Averager::reset (averager.cpp:27-34) / constructor state (averager.cpp:7-12)
+  int reset_averager() {
+    const size_t n = cfg.fft_size, Y = cfg.grouping_y;
+    CU(cudaMemsetAsync(d_sum.p, 0, sizeof(float) * n, stream));
+    for (auto& r : d_ring) CU(cudaMemsetAsync(r.p, 0, sizeof(float) * Y * n, stream));
+    std::vector<float> nd(n, kNoData);
+    CU(cudaMemcpyAsync(d_avg_last.p, nd.data(), sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    avg_frames = 0;
+    ring_cur = 0;
+    return 0;
+  }
+
+  // ---- worker ----
+  void worker_loop() {
+    cudaSetDevice(engine->device);
+    for (;;) {
+      int idx;
+      {
+        std::unique_lock<std::mutex> lk(qmutex);
+        qcv.wait(lk, [&] { return stop_worker || !queue.empty(); });
+        if (queue.empty()) return;
+        idx = queue.front();
+      }
+      const int rc = finish_chunk(slots[idx]);
+      {
+        std::lock_guard<std::mutex> lk(qmutex);
+        if (rc && !worker_rc) {
+          worker_rc = rc;
+          worker_error = g_error;
+        }
+        queue.pop_front();
+        slots[idx].busy = false;
+      }
+      qcv.notify_all();
+    }
+  }
+  void shutdown_worker() {
+    if (worker.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(qmutex);
+        stop_worker = true;
+      }
+      qcv.notify_all();
+      worker.join();
+    }
+  }
+  // wait until every enqueued chunk has been finished; surfaces a worker error once
+  int drain() {
+    if (!async_mode) return 0;
+    std::unique_lock<std::mutex> lk(qmutex);
+    qcv.wait(lk, [&] { return queue.empty(); });
+    if (worker_rc) {
+      const int rc = worker_rc;
+      g_error = worker_error;
+      worker_rc = 0;
+      return rc;
+    }
+    return 0;
+  }
+  int wait_slot_free(int idx) {
+    if (!async_mode) return 0;
+    std::unique_lock<std::mutex> lk(qmutex);
+    qcv.wait(lk, [&] { return !slots[idx].busy; });
+    return 0;
+  }
+
+  int enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out);
+  int finish_chunk(PushSlot& s);
+  int push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
+    const int idx = async_mode ? next_slot : 0;
+    int rc = wait_slot_free(idx);
+    if (rc) return rc;
+    PushSlot& s = slots[idx];
+    if ((rc = enqueue_chunk(s, iq_dev, frames, t0_ms, period_ms, frame_offset, out))) return rc;
+    if (!async_mode) return finish_chunk(s);
+    {
+      std::lock_guard<std::mutex> lk(qmutex);
+      s.busy = true;
+      queue.push_back(idx);
+    }
+    qcv.notify_all();
+    next_slot = (next_slot + 1) % kPushSlots;
+    return 0;
+  }
+};
+
+// GPU half: everything is enqueued on `stream`; the host does not wait.
+int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
+  const int n = cfg.fft_size, Y = cfg.grouping_y;
+  const int T = static_cast<int>(frames);
+  const size_t bytes_per_sample = cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
+  int rc;
+  s.dense_q_on = out && out->noise_sub_db;
+  s.dense_avg_on = out && out->avg_db;
+  s.dense_box_on = out && out->box_db;
+  if (s.dense_q_on && (rc = s.dense_q.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+  if (s.dense_avg_on && (rc = s.dense_avg.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+  if (s.dense_box_on && (rc = s.dense_box.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+  if (profiling) {
+    for (auto& e : s.ev) {
+      if (!e) CU(cudaEventCreate(&e));
+    }
+  }
+
+  // ---- K1: spectra ----
+  SpectralArgs sa{};
+  sa.iq = iq_dev;
+  sa.frame_stride_bytes = static_cast<long long>(cfg.frame_stride_samples) * bytes_per_sample;
+  sa.n_frames = T;
+  sa.wscale = tables.wscale.p;
+  sa.twiddle = tables.twiddle.p;
+  sa.inv_fs = 1.0f / static_cast<float>(cfg.sample_rate_hz);
+  sa.psd_db = s.psd.p;
+  sa.power_lin = nullptr;
+  sa.peak_index = s.peak_idx.p;
+  sa.peak_value = s.peak_val.p;
+  if (profiling) CU(cudaEventRecord(s.ev[0], stream));
+  if ((rc = launch_spectrum(engine, n, cfg.iq_format, sa, stream))) return rc;
+  if (profiling) CU(cudaEventRecord(s.ev[1], stream));
+
+  // ---- plan the spectrogram emissions of this chunk from the clock (Spectrogram::send, spectrogram.cpp:62-75) ----
+  int n_emit = 0;
+  int emit_frames[kMaxSpecEmits] = {0}, emit_divs[kMaxSpecEmits] = {0};
+  SpectroSlot* ss = nullptr;
+  const int M = cfg.spectrogram_out_size;
+  s.emit_time.clear();
+  if (M > 0) {
+    auto it = spectro.find(center);
+    if (it == spectro.end()) {
+      it = spectro.emplace(center, SpectroSlot{}).first;
+      if ((rc = it->second.sum.alloc(M))) return rc;
+      CU(cudaMemsetAsync(it->second.sum.p, 0, sizeof(float) * M, stream));
+      it->second.counter = 0;  // the reference leaves m_counter uninitialised (spectrogram.cpp:9); defined as 0
+      it->second.last_send = host::frame_time(t0_ms, period_ms, frame_offset);  // Container ctor: getTime()
+    }
+    ss = &it->second;
+    for (int t = 0; t < T; ++t) {
+      const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
+      ss->counter++;
+      if (ss->last_send + cfg.spectrogram_interval_ms < now) {
+        if (n_emit >= kMaxSpecEmits) return fail(B2S_E_INVALID, "more than %d spectrogram rows fall into one push chunk; push fewer frames or raise the interval", kMaxSpecEmits);
+        emit_frames[n_emit] = t;
+        emit_divs[n_emit] = ss->counter;
+        ++n_emit;
+        s.emit_time.push_back(now);
+        ss->counter = 0;
+        ss->last_send = now;
+      }
+    }
+    if (n_emit > 0 && (rc = s.spec_rows.alloc(static_cast<size_t>(n_emit) * M))) return rc;
+  }
+
+  // ---- K2: noise / averager / boxcar / detect / spectrogram ----
+  NoiseSlot* ns = nullptr;
+  if ((rc = noise_slot(&ns))) return rc;
+  CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
+  CU(cudaMemsetAsync(s.max_count.p, 0, sizeof(int), stream));
+  const int ring_in = ring_cur, ring_out = (ring_cur + 1) % kRings;
+  DetectArgs da{};
+  da.n = n;
+  da.n_frames = T;
+  da.group_y = Y;
+  da.group_x = cfg.grouping_x;
+  da.psd = s.psd.p;
+  da.threshold = ns->threshold.p;
+  da.noise_samples = ns->ready ? cfg.learn_frames : ns->samples;
+  da.learn_frames = cfg.learn_frames;
+  da.avg_sum = d_sum.p;
+  da.ring_in = d_ring[ring_in].p;
+  da.ring_out = d_ring[ring_out].p;
+  da.avg_frames = avg_frames;
+  da.avg_last = d_avg_last.p;
+  da.checkpoints = s.ckpt.p;
+  da.detect_level = std::min(cfg.start_level, cfg.stop_level);
+  da.slots = d_slots.p;
+  da.slot_count = d_slot_count.p;
+  da.slot_capacity = slot_capacity;
+  da.spec_out = M;
+  da.spec_sum = ss ? ss->sum.p : nullptr;
+  da.n_emit = n_emit;
+  for (int i = 0; i < n_emit; ++i) {
+    da.emit_frame[i] = emit_frames[i];
+    da.emit_div[i] = emit_divs[i];
+  }
+  da.spec_rows = s.spec_rows.p;
+  da.dense_q = s.dense_q_on ? s.dense_q.p : nullptr;
+  da.dense_avg = s.dense_avg_on ? s.dense_avg.p : nullptr;
+  da.dense_box = s.dense_box_on ? s.dense_box.p : nullptr;
+  {
+    const int half = cfg.grouping_x / 2;
+    const int hp = (half + 3) & ~3;
+    const int width = kDetectBinsPerCta + 2 * hp;
+    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * 3 * kDetectTileFrames +
+                        sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta;
+    const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+    static bool configured = false;
+    if (!configured) {
+      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    if (profiling) CU(cudaEventRecord(s.ev[2], stream));
+    if (half == 10 && Y == 21) {
+      k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da);
+    } else {
+      k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da);
+    }
+    CU(cudaGetLastError());
+    // order the per-frame slot lists by bin into one dense array
+    k_entries_prefix<<<1, 1024, 0, stream>>>(d_slot_count.p, slot_capacity, T, s.offsets.p, s.max_count.p);
+    CU(cudaGetLastError());
+    k_entries_sort<<<(T * 32 + 255) / 256, 256, 0, stream>>>(d_slots.p, d_slot_count.p, slot_capacity, T, s.offsets.p, s.sorted.p);
+    CU(cudaGetLastError());
+    if (profiling) CU(cudaEventRecord(s.ev[3], stream));
+  }
+  CU(cudaEventRecord(s.gpu_done, stream));
+
+  // context for the finish half
+  s.T = T;
+  s.t0_ms = t0_ms;
+  s.period_ms = period_ms;
+  s.frame_offset = frame_offset;
+  s.noise_samples = da.noise_samples;
+  s.avg_frames_before = avg_frames;
+  s.ring_before = ring_in;
+  s.threshold = ns->threshold.p;
+  s.center = center;
+  s.n_emit = n_emit;
+  s.out = out;
+  s.thr_host_valid = false;
+  // host mirrors of the scalar state advance at enqueue time (they do not depend on the results)
+  if (!ns->ready) {
+    ns->samples = std::min(ns->samples + T, cfg.learn_frames);
+    ns->ready = ns->samples >= cfg.learn_frames;
+  }
+  avg_frames = std::min(avg_frames + T, Y);
+  ring_cur = ring_out;
+  prof.frames += T;
+  prof.spectral_launches += 1;
+  prof.detect_launches += 1;  // k_detect (+ the two small list-ordering kernels, timed with it)
+  return 0;
+}
+
+// Result half: blocks on the slot's GPU work, then runs the host bookkeeping. Uses fstream() for its own transfers.
+int b2s_band::finish_chunk(PushSlot& s) {
+  cur = &s;
+  cudaStream_t st = fstream();
+  const int n = cfg.fft_size, T = s.T, M = cfg.spectrogram_out_size;
+  int rc;
+  b2s_result* out = s.out;
+  if (st != stream) CU(cudaStreamWaitEvent(st, s.gpu_done, 0));
+  int* h_off = s.h_offsets.p;
+  int* h_max = s.h_offsets.p + max_frames + 1;
+  CU(cudaMemcpyAsync(h_off, s.offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_max, s.max_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int n_entries = h_off[T];
+  prof.d2h_bytes += sizeof(int) * (T + 2);
+  if (profiling && s.ev[0]) {
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+    prof.spectral_ms += ms;
+    CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
+    prof.detect_ms += ms;
+  }
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (*h_max > slot_capacity) return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries; detect_capacity is %d per frame", *h_max, slot_capacity);
+  if (n_entries > 0) {
+    if ((rc = s.h_entries.alloc(n_entries))) return rc;
+    CU(cudaMemcpyAsync(s.h_entries.p, s.sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
+  }
+  const bool every = out && out->frame_tx_count;
+  std::vector<Tracker::FrameState> states;
+  tracker.p.center = s.center;
+  rc = tracker.run(s.h_entries.p, h_off, T, s.t0_ms, s.period_ms, s.frame_offset, *this, every, states);
+  if (rc) return rc;
+  prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+
+  // the mailbox after the last frame of this chunk
+  mailbox_count = 0;
+  if (!states.empty() && states.back().frame == T - 1) {
+    const int total = tracker.sorted_transmissions(states.back(), mailbox, B2S_MAX_TX);
+    mailbox_count = std::min(total, B2S_MAX_TX);
+  }
+  stat_entries += n_entries;
+  stat_rows += s.n_emit;
+  if (out) {
+    out->n_detect_entries += n_entries;
+    out->n_spectrogram_rows += s.n_emit;
+    if (every) {
+      for (int t = 0; t < T; ++t) out->frame_tx_count[s.frame_offset + t] = 0;
+      for (const auto& fs : states) {
+        out->frame_tx_count[s.frame_offset + fs.frame] =
+            tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (s.frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
+      }
+    }
+    out->n_transmissions = mailbox_count;
+    std::memcpy(out->transmissions, mailbox, sizeof(b2s_transmission) * mailbox_count);
+    if (out->peak_index) CU(cudaMemcpyAsync(out->peak_index + s.frame_offset, s.peak_idx.p, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
+    if (out->peak_value) CU(cudaMemcpyAsync(out->peak_value + s.frame_offset, s.peak_val.p, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
+    const size_t row_bytes = sizeof(float) * static_cast<size_t>(T) * n, off = s.frame_offset * n;
+    if (out->psd_db) CU(cudaMemcpyAsync(out->psd_db + off, s.psd.p, row_bytes, cudaMemcpyDeviceToHost, st));
+    if (out->noise_sub_db) CU(cudaMemcpyAsync(out->noise_sub_db + off, s.dense_q.p, row_bytes, cudaMemcpyDeviceToHost, st));
+    if (out->avg_db) CU(cudaMemcpyAsync(out->avg_db + off, s.dense_avg.p, row_bytes, cudaMemcpyDeviceToHost, st));
+    if (out->box_db) CU(cudaMemcpyAsync(out->box_db + off, s.dense_box.p, row_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  if (s.n_emit > 0) {
+    std::vector<int8_t> rows(static_cast<size_t>(s.n_emit) * M);
+    CU(cudaMemcpyAsync(rows.data(), s.spec_rows.p, rows.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < s.n_emit; ++i) {
+      sent.push_back(SentRow{s.emit_time[i], s.center, std::vector<int8_t>(rows.begin() + static_cast<size_t>(i) * M, rows.begin() + static_cast<size_t>(i + 1) * M)});
+    }
+  }
+  CU(cudaStreamSynchronize(st));
+  cur = nullptr;
+  return 0;
+}

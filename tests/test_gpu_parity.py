@@ -271,6 +271,48 @@ def test_fast_path_equals_dense_path_bitwise(engine):
     assert np.array_equal(tf_, ts_) and np.array_equal(rf, rs) and len(tf_) >= 2
 
 
+def test_async_mode_equals_sync_mode(engine):
+    """B2S_FLAG_ASYNC (bookkeeping of push k on a worker thread while push k+1 is in the kernels) must leave the same
+    state and deliver the same mailbox, signals and spectrogram rows as the synchronous mode, for host and device input."""
+    import torch
+
+    n, fs, frames, learn = 1024, 1_024_000, 600, 40
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    cfg.spectrogram_interval_ms = 40
+    cfg.max_frames_per_push = 64
+    sync = b2s.Band(engine, cfg)
+    acfg = b2s.BandConfig.from_buffer_copy(cfg)
+    acfg.flags |= b2s.FLAG_ASYNC
+    asyn = b2s.Band(engine, acfg)
+    dcfg = b2s.BandConfig.from_buffer_copy(acfg)
+    dcfg.flags |= b2s.FLAG_IQ_ON_DEVICE
+    adev = b2s.Band(engine, dcfg)
+    iq_dev = torch.from_numpy(iq).cuda()
+    sizes, k, i = [50, 64, 7, 120, 33, 64, 200], 0, 0
+    mail_sync = None
+    while k < frames:
+        m = min(sizes[i % len(sizes)], frames - k)
+        i += 1
+        mail_sync = sync.push(iq[k * 2 * n :], m, 500 + k, period).transmissions
+        asyn.push_raw(iq[k * 2 * n :].ctypes.data, m, 500 + k, period)
+        adev.push_raw(iq_dev.data_ptr() + k * 2 * n, m, 500 + k, period)
+        k += m
+    for band in (asyn, adev):
+        res = band.sync()
+        mail = [(t.shift_hz, t.flush, t.key, t.power) for t in res.transmissions[: res.n_transmissions]]
+        assert mail == mail_sync
+        for a, b in zip(sync.get_averager(), band.get_averager()):
+            assert np.array_equal(a, b)
+        for a, b in zip(sync.get_signals(), band.get_signals()):
+            assert np.array_equal(a, b)
+        ts, _, rs = sync.get_spectrogram(consume=False)
+        ta, _, ra = band.get_spectrogram()
+        assert np.array_equal(ts, ta) and np.array_equal(rs, ra) and len(ts) >= 5
+    assert len(sync.get_signals()[0]) >= 0 and mail_sync is not None
+    with pytest.raises(b2s.B2SError):
+        asyn.push(iq, 10, 5000, period)  # async mode takes no per-push result structure
+
+
 def test_chunked_pushes_equal_one_push(engine):
     """State carried across b2s_band_push calls (ring hand-over, noise, tracker, spectrogram) — pushes of 1..97 frames,
     some shorter than the Averager depth — must reproduce the single-push result bit for bit."""
