@@ -494,6 +494,10 @@ int b2s_band_reset(b2s_band* b) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(b->stream));
   b->tracker.reset();
+  {
+    std::lock_guard<std::mutex> lk(b->qmutex);
+    b->published_keys.clear();
+  }
   return b->reset_averager();
 }
 

@@ -40,8 +40,13 @@ struct PushSlot {
   DevBuf<int> peak_idx, offsets, max_count;
   DevBuf<DetectEntry> sorted;
   DevBuf<signed char> spec_rows;
-  PinBuf<int> h_offsets;
+  DevBuf<unsigned int> watch_max;
+  DevBuf<int> cand_flag;
+  PinBuf<int> h_offsets, h_cand_flag;
+  PinBuf<unsigned int> h_watch_max;
   PinBuf<DetectEntry> h_entries;
+  int n_watch = 0;
+  int watch_key[kMaxWatch] = {0};
   cudaEvent_t gpu_done = nullptr, ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // context of the chunk in flight
   bool busy = false;
@@ -61,7 +66,7 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
-    h_offsets.release(); h_entries.release();
+    h_offsets.release(); h_entries.release(); watch_max.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
     if (gpu_done) cudaEventDestroy(gpu_done);
     for (auto& e : ev) {
       if (e) cudaEventDestroy(e);
@@ -116,6 +121,8 @@ struct b2s_band : public DeviceQueries {
   bool stop_worker = false;
   int worker_rc = 0;
   std::string worker_error;
+
+  std::vector<int> published_keys;  // signal-map keys after the most recently finished chunk (guarded by qmutex)
 
   PushSlot* cur = nullptr;  // slot whose finish half is running (DeviceQueries context)
   cudaStream_t fstream() const { return async_mode ? finish_stream : stream; }
@@ -295,6 +302,10 @@ struct b2s_band : public DeviceQueries {
       if ((rc = s.max_count.alloc(1))) return rc;
       if ((rc = s.h_offsets.alloc(max_frames + 2))) return rc;
       if ((rc = s.h_entries.alloc(static_cast<size_t>(max_frames) * 64))) return rc;
+      if ((rc = s.watch_max.alloc(static_cast<size_t>(max_frames) * kMaxWatch))) return rc;
+      if ((rc = s.cand_flag.alloc(max_frames))) return rc;
+      if ((rc = s.h_watch_max.alloc(static_cast<size_t>(max_frames) * kMaxWatch))) return rc;
+      if ((rc = s.h_cand_flag.alloc(max_frames))) return rc;
       CU(cudaEventCreateWithFlags(&s.gpu_done, cudaEventDisableTiming));
     }
     if ((rc = d_sum.alloc(n))) return rc;
@@ -493,6 +504,13 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   if ((rc = noise_slot(&ns))) return rc;
   CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
   CU(cudaMemsetAsync(s.max_count.p, 0, sizeof(int), stream));
+  CU(cudaMemsetAsync(s.cand_flag.p, 0, sizeof(int) * T, stream));
+  {
+    std::lock_guard<std::mutex> lk(qmutex);
+    s.n_watch = std::min<int>(static_cast<int>(published_keys.size()), kMaxWatch);
+    for (int i = 0; i < s.n_watch; ++i) s.watch_key[i] = published_keys[i];
+  }
+  if (s.n_watch > 0) CU(cudaMemsetAsync(s.watch_max.p, 0, sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch, stream));
   const int ring_in = ring_cur, ring_out = (ring_cur + 1) % kRings;
   DetectArgs da{};
   da.n = n;
@@ -513,6 +531,12 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.slots = d_slots.p;
   da.slot_count = d_slot_count.p;
   da.slot_capacity = slot_capacity;
+  da.n_watch = s.n_watch;
+  for (int i = 0; i < s.n_watch; ++i) da.watch_key[i] = s.watch_key[i];
+  da.group_size = cfg.group_size_bins;
+  da.start_level = cfg.start_level;
+  da.watch_max = s.watch_max.p;
+  da.cand_flag = s.cand_flag.p;
   da.spec_out = M;
   da.spec_sum = ss ? ss->sum.p : nullptr;
   da.n_emit = n_emit;
@@ -591,9 +615,11 @@ int b2s_band::finish_chunk(PushSlot& s) {
   int* h_max = s.h_offsets.p + max_frames + 1;
   CU(cudaMemcpyAsync(h_off, s.offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h_max, s.max_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.h_cand_flag.p, s.cand_flag.p, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
+  if (s.n_watch > 0) CU(cudaMemcpyAsync(s.h_watch_max.p, s.watch_max.p, sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   const int n_entries = h_off[T];
-  prof.d2h_bytes += sizeof(int) * (T + 2);
+  prof.d2h_bytes += sizeof(int) * (2 * T + 2) + (s.n_watch > 0 ? sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch : 0);
   if (profiling && s.ev[0]) {
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
@@ -612,8 +638,14 @@ int b2s_band::finish_chunk(PushSlot& s) {
   const bool every = out && out->frame_tx_count;
   std::vector<Tracker::FrameState> states;
   tracker.p.center = s.center;
-  rc = tracker.run(s.h_entries.p, h_off, T, s.t0_ms, s.period_ms, s.frame_offset, *this, every, states);
+  Tracker::Watch watch{s.n_watch, s.watch_key, s.h_watch_max.p, s.h_cand_flag.p};
+  rc = tracker.run(s.h_entries.p, h_off, T, s.t0_ms, s.period_ms, s.frame_offset, *this, every, watch, states);
   if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(qmutex);
+    published_keys.clear();
+    for (const auto& kv : tracker.signals) published_keys.push_back(kv.first);
+  }
   prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 
   // the mailbox after the last frame of this chunk

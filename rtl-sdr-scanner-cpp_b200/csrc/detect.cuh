@@ -15,6 +15,7 @@
 // parallel. b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
 #pragma once
 #include <cstdio>
+#include <cstring>
 
 #include "b2s_device.cuh"
 
@@ -25,6 +26,7 @@ constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
 constexpr int kDetectThreads = 512;
 constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
 constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
+constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
 
 struct DetectEntry {  // one bin whose boxcar power reached min(start, stop) in one frame
@@ -59,6 +61,16 @@ struct DetectArgs {
   // spectrogram
   int spec_out;           // M (0 = off)
   float* spec_sum;        // [M]
+  // watch list: the signal-map keys known when the push was enqueued. For each, K2 reports the maximum of the boxcar row
+  // over [key - g/2, key + g/2] per frame (getMaxIndex(avgPower, N, key, groupSize) of Transmission::updateSignals,
+  // transmission.cpp:114-117) and, per frame, whether any bin at or above the start level lies outside every key's
+  // containsWithMargin interval (collection_utils.h:17-27) — i.e. whether addSignals could create a signal at all.
+  int n_watch;
+  int watch_key[kMaxWatch];
+  int group_size;            // m_groupSize in bins
+  float start_level;
+  unsigned int* watch_max;   // [T][kMaxWatch] order-preserving encoding of the float maximum (0 = nothing written)
+  int* cand_flag;            // [T] set to 1 when an uncovered candidate exists
   // rows to emit during this push, planned by the host from the frame clock (Spectrogram::send, spectrogram.cpp:62-75).
   // Carried in the kernel arguments so that no small host->device copy sits on the critical path behind the bulk IQ copy.
   int n_emit;                      // <= kMaxSpecEmits
@@ -108,6 +120,23 @@ __device__ __forceinline__ float div_const_fast(float x) {
   const float q = __fmul_rn(x, r);
   const float e = __fmaf_rn(-q, d, x);
   return __fmaf_rn(e, r, q);
+}
+
+// order-preserving map float -> unsigned (so atomicMax on the image is max on the floats); never yields 0 for a real number
+__host__ __device__ __forceinline__ unsigned int float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  const unsigned int b = __float_as_uint(f);
+#else
+  unsigned int b;
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+inline float ordered_to_float(unsigned int u) {
+  const unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
 }
 
 constexpr int kBoxSegment = 8;  // bins per boxcar segment (segments are aligned to multiples of 8 bins)
@@ -369,12 +398,37 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
           box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return row[hp + (bb - j0)]; }, bin, n, half);
         }
       }
-      if (!a.dense_box) {
-        float top = box[0];
+      float top = box[0];
 #pragma unroll
-        for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
-        if (top < a.detect_level) continue;  // nothing to report from these 8 bins
+      for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
+      // watched keys: window maxima over ALL bins (also below the detection level), and the uncovered-candidate flag
+      if (a.n_watch > 0 || top >= a.start_level) {
+        const int gh = a.group_size / 2, margin = (a.group_size % 2 == 0) ? gh : gh + 1;
+        unsigned int covered = 0;  // bit k: bin0 + k lies inside some key's containsWithMargin interval
+        for (int w = 0; w < a.n_watch; ++w) {
+          const int key = a.watch_key[w];
+          if (bin0 + SEG - 1 >= key - gh && bin0 <= key + gh) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) {
+              const int bin = bin0 + k;
+              if (bin < n && bin >= key - gh && bin <= key + gh) m = fmaxf(m, box[k]);
+            }
+            if (m > -INFINITY) atomicMax(a.watch_max + static_cast<size_t>(t) * kMaxWatch + w, float_to_ordered(m));
+          }
+          if (bin0 + SEG - 1 >= key - margin && bin0 <= key + margin) {
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) covered |= (bin0 + k >= key - margin && bin0 + k <= key + margin) ? (1u << k) : 0u;
+          }
+        }
+        if (top >= a.start_level) {
+          bool uncovered = false;
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) uncovered |= (bin0 + k < n) && box[k] >= a.start_level && !((covered >> k) & 1u);
+          if (uncovered) a.cand_flag[t] = 1;
+        }
       }
+      if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
 #pragma unroll
       for (int k = 0; k < SEG; ++k) {
         const int bin = bin0 + k;

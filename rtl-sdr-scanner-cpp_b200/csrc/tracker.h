@@ -85,24 +85,47 @@ class Tracker {
     std::vector<char> power_known;
   };
 
+  // What K2 already reduced for the keys that were live when the chunk was enqueued (DetectArgs watch list):
+  // max[t * kMaxWatch + i] = order-preserving image of max(boxcar row over key_i's window) in frame t (0 = nothing),
+  // flag[t] != 0 when some bin >= start level lies outside every watched key's margin interval.
+  struct Watch {
+    int n = 0;
+    const int* key = nullptr;
+    const unsigned int* max = nullptr;
+    const int* flag = nullptr;
+  };
+
   // entries: the detection entries of the chunk ordered by (frame, bin); frame_begin[t]..frame_begin[t+1] index them.
   // Produces one FrameState per frame that ends with at least one live signal (only the last frame unless
   // need_every_frame). Frame t of this chunk is frame (frame_offset + t) of the caller's push and is stamped accordingly.
   int run(const DetectEntry* entries, const int* frame_begin, size_t n_frames, int64_t t0_ms, double period_ms, size_t frame_offset, DeviceQueries& dev,
-          bool need_every_frame, std::vector<FrameState>& out) {
+          bool need_every_frame, const Watch& watch, std::vector<FrameState>& out) {
     out.clear();
     const int half_g = p.group_size / 2;
+    // which watch slot (if any) covers a live key; how many watched keys are still alive. While ALL watched keys are
+    // alive the current margins cover at least what K2 assumed, so flag[t] == 0 proves that addSignals cannot fire.
+    auto watch_slot = [&](int key) {
+      for (int i = 0; i < watch.n; ++i) {
+        if (watch.key[i] == key) return i;
+      }
+      return -1;
+    };
+    int watched_alive = 0;
+    for (const auto& kv : signals) watched_alive += watch_slot(kv.first) >= 0 ? 1 : 0;
     for (size_t t = 0; t < n_frames; ++t) {
       const int e0 = frame_begin[t], e1 = frame_begin[t + 1];
-      if (e0 == e1 && signals.empty()) continue;
+      const bool flags_valid = watch.flag != nullptr && watched_alive == watch.n;
+      if (signals.empty() && (flags_valid ? watch.flag[t] == 0 : e0 == e1)) continue;
       const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
       // ---- addSignals ----
       // A candidate only changes the map when no key lies within the margin; the power ordering of the candidates
       // (std::sort in the reference) matters only then, so the list is built and ordered lazily.
       bool any_new = false;
-      for (int e = e0; e < e1 && !any_new; ++e) {
-        const DetectEntry& d = entries[e];
-        if (p.start_level <= d.value && !host::key_within_margin(signals, d.bin, p.group_size) && in_range(d.bin) && !ignored(d.bin)) any_new = true;
+      if (!flags_valid || watch.flag[t] != 0) {
+        for (int e = e0; e < e1 && !any_new; ++e) {
+          const DetectEntry& d = entries[e];
+          if (p.start_level <= d.value && !host::key_within_margin(signals, d.bin, p.group_size) && in_range(d.bin) && !ignored(d.bin)) any_new = true;
+        }
       }
       if (any_new) {
         cand_.clear();
@@ -117,36 +140,45 @@ class Tracker {
             int key = idx;
             const int rc = best_index(idx, static_cast<int>(t), dev, &key);
             if (rc != 0) return rc;
-            signals.insert({key, TrackedSignal{now, now, 0.0f}});
+            if (signals.insert({key, TrackedSignal{now, now, 0.0f}}).second && watch_slot(key) >= 0) watched_alive++;
           }
         }
       }
       if (signals.empty()) continue;
       // ---- updateSignals: window maximum of the boxcar row around every key, then clearSignals ----
       for (auto it = signals.begin(); it != signals.end();) {
-        const int lo = std::max(0, it->first - half_g), hi = std::min(p.n - 1, it->first + half_g);
-        int a = e0, b = e1;
-        while (a < b) {  // first entry of this frame with bin >= lo
-          const int m = (a + b) / 2;
-          if (entries[m].bin < lo) a = m + 1; else b = m;
-        }
-        bool found = false;
-        float best = 0.0f;
-        for (int e = a; e < e1 && entries[e].bin <= hi; ++e) {
-          if (!found || entries[e].value > best) {
-            best = entries[e].value;
-            found = true;
-          }
-        }
         TrackedSignal& s = it->second;
-        if (found) {
-          s.power = best;  // Signal::newData: m_power = avgPower
+        const int ws = watch_slot(it->first);
+        const unsigned int image = (ws >= 0 && watch.max) ? watch.max[t * kMaxWatch + ws] : 0u;
+        if (image != 0u) {
+          const float best = ordered_to_float(image);  // exact window maximum, also below the detection level
+          s.power = best;                              // Signal::newData: m_power = avgPower
           if (p.stop_level <= best) s.last = now;
         } else {
-          // every bin of the window is below min(start, stop): neither level test can pass; only m_power is unknown
-          s.power = std::nanf("");
+          const int lo = std::max(0, it->first - half_g), hi = std::min(p.n - 1, it->first + half_g);
+          int a = e0, b = e1;
+          while (a < b) {  // first entry of this frame with bin >= lo
+            const int m = (a + b) / 2;
+            if (entries[m].bin < lo) a = m + 1; else b = m;
+          }
+          bool found = false;
+          float best = 0.0f;
+          for (int e = a; e < e1 && entries[e].bin <= hi; ++e) {
+            if (!found || entries[e].value > best) {
+              best = entries[e].value;
+              found = true;
+            }
+          }
+          if (found) {
+            s.power = best;
+            if (p.stop_level <= best) s.last = now;
+          } else {
+            // every bin of the window is below min(start, stop): neither level test can pass; only m_power is unknown
+            s.power = std::nanf("");
+          }
         }
         if (s.last + p.timeout <= now || s.first + p.max_time <= now) {
+          if (ws >= 0) watched_alive--;
           it = signals.erase(it);
         } else {
           ++it;
