@@ -552,13 +552,13 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * ((kDetectBuffers + 3) * kDetectTileFrames * width + width) + sizeof(int) * 3 * kDetectTileFrames +
+    const size_t smem = sizeof(float) * (kDetectBuffers + 4) * kDetectTileFrames * width + sizeof(int) * 2 * kDetectTileFrames +
                         sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       configured = true;
     }
     if (profiling) CU(cudaEventRecord(s.ev[2], stream));

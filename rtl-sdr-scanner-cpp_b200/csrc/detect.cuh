@@ -190,122 +190,192 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // PSD tiles of kDetectTileFrames rows are streamed into shared memory with cp.async two tiles ahead; one thread per
 // column marches the tile through noise -> Averager (the only serial chain: two dependent FADDs per frame); then all
 // threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+constexpr int kMarchThreads = 192;                              // warps 0-5: one thread per column (<= 192 columns)
+constexpr int kBoxThreads = kDetectThreads - kMarchThreads;     // warps 6-15: boxcar + threshold + emission
+constexpr int kBarMarch = 1, kBarBox = 2, kBarFull = 3 /*,4*/, kBarEmpty = 5 /*,6*/;
+
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
-// or 0 / -1 for the generic runtime-parameter instantiation. The specialised instantiation runs steady-state tiles
-// (no learning frame in the tile or its look-back, t0 >= Y, full tile, no dense debug rows) through a fast path that
-// splits the work by dependency: (1a) all threads subtract the noise threshold elementwise, (1b) one thread per
-// column runs ONLY the serial part (m_sum -= leaving; m_sum += entering; m_average = m_sum / Y) out of shared memory,
-// (2) all threads evaluate boxcar + threshold. Every other tile takes the generic per-column path. Both paths execute
-// the same float operations in the same order, so they are interchangeable bit for bit (tested).
+// or 0 / -1 for the generic runtime-parameter instantiation.
+//
+// Warp-specialised, software-pipelined over tiles of 32 frames:
+//   MARCH warps (one thread per column): stream the PSD tile in with cp.async, NoiseLearner subtraction, the serial
+//     Averager chain (m_sum -= leaving; m_sum += entering; m_average = m_sum / Y), spectrogram accumulation; they write the
+//     tile of averaged values into one of two shared buffers and move on to the next tile.
+//   BOX warps: boxcar over 8-bin segments + threshold + watched-window maxima for the tile the march warps finished one
+//     step earlier; detection entries are staged in shared memory and flushed with one global atomic per (CTA, frame).
+// The two groups meet only through FULL/EMPTY named barriers on the double-buffered average tile, so the serial chain of
+// tile i+1 overlaps the throughput work of tile i. Steady-state tiles (no learning frame, ring look-back inside the push,
+// full tile, no dense debug rows) take a branch-free register-resident march; all others a generic per-column march with
+// the same float operations in the same order (bit-identical, tested).
 template <int Y_T, int HALF_T>
 __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int half = HALF_T >= 0 ? HALF_T : a.group_x / 2;
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
-  const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA
+  const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA (<= kMarchThreads)
   const int tile_elems = kDetectTileFrames * width;
   float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width] raw PSD (cp.async target)
   float* q_tiles = psd_tiles + kDetectBuffers * tile_elems;         // [2][TF][width] noise-subtracted rows (current, previous)
-  float* __restrict__ avg_tile = q_tiles + 2 * tile_elems;          // [TF][width]
-  float* thr_s = avg_tile + tile_elems;                             // [width]
-  int* slot_tile = reinterpret_cast<int*>(thr_s + width);           // [TF] spectrogram slot of each frame of the tile
-  int* stage_count = slot_tile + kDetectTileFrames;                 // [TF] detection entries staged per frame of the tile
+  float* avg_tiles = q_tiles + 2 * tile_elems;                      // [2][TF][width] averaged rows handed to the box warps
+  int* stage_count = reinterpret_cast<int*>(avg_tiles + 2 * tile_elems);  // [TF] detection entries staged per frame of the tile
   int* stage_base = stage_count + kDetectTileFrames;                // [TF] where this CTA's block starts in the frame's slot list
   DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_base + kDetectTileFrames);  // [TF][kDetectBinsPerCta]
+  __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];    // watched keys that touch this CTA's bins
 
   const int n = a.n, T = a.n_frames, Y = Y_T > 0 ? Y_T : a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
   const int col0 = j0 - hp;  // bin of column 0
   const int tid = threadIdx.x;
-  const int j = col0 + tid;  // my column's bin (march role)
-  const bool active = tid < width && j >= 0 && j < n;
-  const bool owner = active && tid >= hp && tid < hp + kDetectBinsPerCta;
   const int n_tiles = (T + kDetectTileFrames - 1) / kDetectTileFrames;
-  const int chunks_per_row = width / 4;
   const bool dense = a.dense_q || a.dense_avg || a.dense_box;
 
-  auto issue_tile = [&](int tile) {
-    if (tile < n_tiles) {
-      float* dst = psd_tiles + (tile % kDetectBuffers) * tile_elems;
-      const int t_base = tile * kDetectTileFrames;
-      for (int c = tid; c < kDetectTileFrames * chunks_per_row; c += kDetectThreads) {
-        const int f = c / chunks_per_row, x = (c - f * chunks_per_row) * 4;
-        const int t = t_base + f, col = col0 + x;
-        if (t < T && col >= 0 && col + 3 < n) cp_async16(dst + f * width + x, a.psd + static_cast<size_t>(t) * n + col);
+  // ---- one-time setup (all threads) ----
+  if (tid == 0) {
+    int cnt = 0;
+    const int reach = a.group_size / 2 + 1;
+    for (int w = 0; w < a.n_watch; ++w) {
+      if (a.watch_key[w] + reach >= j0 && a.watch_key[w] - reach < j0 + kDetectBinsPerCta) {
+        rel_key[cnt] = a.watch_key[w];
+        rel_slot[cnt] = w;
+        ++cnt;
       }
     }
-    cp_async_commit();
-  };
-
-  float thr = active ? a.threshold[j] : 0.0f;
-  float sum = active ? a.avg_sum[j] : 0.0f;
-  float last_avg = kNoData;
-  const int d = a.spec_out > 0 ? n / a.spec_out : 0;
-  const bool spec_owner = owner && d > 0 && (j % d) == 0;
-  float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
-  const bool ring_in_smem = Y <= kDetectTileFrames;
-  if (tid < width) thr_s[tid] = thr;
-  if (tid < kDetectTileFrames) stage_count[tid] = 0;
-  if (tid < width && !active) {  // columns outside the row: the boxcar sees the zero-extended row
-    for (int f = 0; f < kDetectTileFrames; ++f) avg_tile[f * width + tid] = 0.0f;
+    rel_n = cnt;
   }
+  if (tid < kDetectTileFrames) stage_count[tid] = 0;
+  if (tid < width && (col0 + tid < 0 || col0 + tid >= n)) {  // columns outside the row: the boxcar sees the zero-extended row
+    for (int f = 0; f < 2 * kDetectTileFrames; ++f) avg_tiles[f * width + tid] = 0.0f;
+  }
+  __syncthreads();
 
-#ifdef B2S_K2_TIMING
-  long long tk[6] = {0, 0, 0, 0, 0, 0};
-  long long c0 = clock64();
-#define TK(i) { long long c1 = clock64(); tk[i] += c1 - c0; c0 = c1; }
-#else
-#define TK(i)
-#endif
-  issue_tile(0);
-  issue_tile(1);
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int t0 = tile * kDetectTileFrames;
-    const int tf = min(kDetectTileFrames, T - t0);
-    cp_async_wait<1>();  // tile `tile` has landed (tile+1 may still be in flight)
-    TK(0)
-    if (tid < kDetectTileFrames) {
-      int slot = -1;
-      if (d > 0) {
-        for (int i = 0; i < a.n_emit; ++i) slot = (a.emit_frame[i] == t0 + tid) ? i : slot;
+  if (tid < kMarchThreads) {
+    // =========================================== MARCH warps ===========================================
+    const int j = col0 + tid;  // my column's bin
+    const bool active = tid < width && j >= 0 && j < n;
+    const bool owner = active && tid >= hp && tid < hp + kDetectBinsPerCta;
+    const int chunks_per_row = width / 4;
+    auto issue_tile = [&](int tile) {
+      if (tile < n_tiles) {
+        float* dst = psd_tiles + (tile % kDetectBuffers) * tile_elems;
+        const int t_base = tile * kDetectTileFrames;
+        for (int c = tid; c < kDetectTileFrames * chunks_per_row; c += kMarchThreads) {
+          const int f = c / chunks_per_row, x = (c - f * chunks_per_row) * 4;
+          const int t = t_base + f, col = col0 + x;
+          if (t < T && col >= 0 && col + 3 < n) cp_async16(dst + f * width + x, a.psd + static_cast<size_t>(t) * n + col);
+        }
       }
-      slot_tile[tid] = slot;
-    }
-    __syncthreads();
-    const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
-    const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
-    float* __restrict__ q_cur = q_tiles + (tile & 1) * tile_elems;
-    const float* __restrict__ q_prev = q_tiles + ((tile & 1) ^ 1) * tile_elems;
-    // steady state: whole tile, ring look-back inside the push, no learning frame in the tile or in its look-back
-    // (the look-back reads q_prev, which every earlier tile wrote — learning frames as -100 — whichever path it took)
-    const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= kDetectTileFrames && Y <= kDetectTileFrames &&
-                        (a.noise_samples + t0 >= a.learn_frames) && !dense;
+      cp_async_commit();
+    };
+    float thr = active ? a.threshold[j] : 0.0f;
+    float sum = active ? a.avg_sum[j] : 0.0f;
+    float last_avg = kNoData;
+    const int d = a.spec_out > 0 ? n / a.spec_out : 0;
+    const bool spec_owner = owner && d > 0 && (j % d) == 0;
+    float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
+    const bool ring_in_smem = Y <= kDetectTileFrames;
+    int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
 
-    if (steady) {
-      // ---- phase 1 (fast): one thread per column. All shared-memory loads of the tile are issued up front and kept
-      // in registers; the only serial work left is m_sum -= leaving; m_sum += entering (2 dependent FADDs per frame) ----
-      if (active) {
-        if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
-        constexpr int YC = Y_T > 0 ? Y_T : 1;
-        constexpr int TF = kDetectTileFrames;
-        const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize
-        float q[TF], lead[YC];
+    issue_tile(0);
+    issue_tile(1);
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int t0 = tile * kDetectTileFrames;
+      const int tf = min(kDetectTileFrames, T - t0);
+      cp_async_wait<1>();                     // my part of tile `tile` has landed (tile+1 may still be in flight)
+      bar_sync(kBarMarch, kMarchThreads);     // ... and everybody else's part; also: tile-1 is fully consumed
+      if (tile >= 2) bar_sync(kBarEmpty + (tile & 1), kDetectThreads);  // the box warps are done with this average buffer
+      const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
+      const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
+      float* __restrict__ q_cur = q_tiles + (tile & 1) * tile_elems;
+      const float* __restrict__ q_prev = q_tiles + ((tile & 1) ^ 1) * tile_elems;
+      float* __restrict__ avg_tile = avg_tiles + (tile & 1) * tile_elems;
+      // planned spectrogram row inside this tile (at most the first one is handled by the fast path)
+      while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
+      const int emit_f = (d > 0 && next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf) ? a.emit_frame[next_emit] - t0 : -1;
+      auto slot_of = [&](int f) {  // planned row emitted after frame t0 + f, or -1
+        int slot = -1;
+        for (int i = next_emit; i < a.n_emit && a.emit_frame[i] <= t0 + f; ++i) slot = (a.emit_frame[i] == t0 + f) ? i : slot;
+        return slot;
+      };
+      // steady state: whole tile, ring look-back inside the push, no learning frame in the tile
+      // (the look-back reads q_prev, which every earlier tile wrote — learning frames as -100 — whichever path it took)
+      const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= kDetectTileFrames && Y <= kDetectTileFrames &&
+                          (a.noise_samples + t0 >= a.learn_frames) && !dense;
+      if (steady) {
+        if (active) {
+          if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
+          constexpr int YC = Y_T > 0 ? Y_T : 1;
+          constexpr int TF = kDetectTileFrames;
+          const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize
+          float q[TF], lead[YC];
 #pragma unroll
-        for (int f = 0; f < TF; ++f) q[f] = cur[f * width + tid];
+          for (int f = 0; f < TF; ++f) q[f] = cur[f * width + tid];
 #pragma unroll
-        for (int f = 0; f < YC; ++f) lead[f] = q_prev[(f - YC + TF) * width + tid];  // rows leaving the ring during the first Y frames
-        // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49); a row is emitted at most once per tile
-        if (d == 1 && owner) {
-          int emit = -1;
+          for (int f = 0; f < YC; ++f) lead[f] = q_prev[(f - YC + TF) * width + tid];  // rows leaving the ring during the first Y frames
+          // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49)
+          if (d == 1 && owner) {
+            if (emit_f < 0) {
 #pragma unroll
-          for (int f = 0; f < TF; ++f) emit = (slot_tile[f] >= 0 && emit < 0) ? f : emit;
-          if (emit < 0) {
+              for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, q[f]);
+            } else {
+              for (int f = 0; f < TF; ++f) {
+                spec = __fadd_rn(spec, cur[f * width + tid]);
+                const int slot = slot_of(f);
+                if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+                  a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
+                  spec = 0.0f;
+                }
+              }
+            }
+          }
 #pragma unroll
-            for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, q[f]);
+          for (int f = 0; f < TF; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
+#pragma unroll
+          for (int f = 0; f < TF; ++f) {
+            const float old = (f >= YC) ? q[f - YC] : lead[f];
+            sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
+            sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
+            const float avg = full ? div_const_fast<YC>(sum) : kNoData;
+            avg_tile[f * width + tid] = avg;
+            q_cur[f * width + tid] = q[f];  // the next tile looks back into this one
+            if (f == TF - 1) last_avg = avg;
+          }
+        }
+      } else if (active) {
+        // ---- generic per-column march (learning frames, first tile of a push, partial tiles, dense debug rows) ----
+        for (int f = 0; f < tf; ++f) {
+          const int t = t0 + f;
+          const float p = cur[f * width + tid];
+          const bool learning = a.noise_samples + t < a.learn_frames;
+          if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
+          const float q = noise_sub(p, thr, learning);
+          q_cur[f * width + tid] = q;  // a later steady tile looks back into this one
+          // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
+          float old;
+          if (t >= Y) {
+            float po;
+            if (ring_in_smem) {
+              po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
+            } else {
+              po = a.psd[static_cast<size_t>(t - Y) * n + j];
+            }
+            old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
           } else {
-            for (int f = 0; f < TF; ++f) {
-              spec = __fadd_rn(spec, cur[f * width + tid]);
-              const int slot = slot_tile[f];
+            old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
+          }
+          if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
+          const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
+          avg_tile[f * width + tid] = avg;
+          last_avg = avg;
+          if (owner) {
+            if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
+            if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
+            if (d == 1) {
+              spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
+              const int slot = emit_f >= 0 ? slot_of(f) : -1;
               if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72
                 a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
                 spec = 0.0f;
@@ -313,190 +383,140 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             }
           }
         }
-#pragma unroll
-        for (int f = 0; f < TF; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
-#pragma unroll
-        for (int f = 0; f < TF; ++f) {
-          const float old = (f >= YC) ? q[f - YC] : lead[f];
-          sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
-          sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
-          const float avg = full ? div_const_fast<YC>(sum) : kNoData;
-          avg_tile[f * width + tid] = avg;
-          q_cur[f * width + tid] = q[f];  // the next tile looks back into this one
-          if (f == TF - 1) last_avg = avg;
+      }
+      if (spec_owner && d > 1) {  // decimating spectrogram: mean of d adjacent raw bins, then accumulate (spectrogram.cpp:50-58)
+        for (int f = 0; f < tf; ++f) {
+          float s = 0.0f;
+          for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + tid + i]);
+          spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));
+          const int slot = emit_f >= 0 ? slot_of(f) : -1;
+          if (slot >= 0) {
+            a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
+            spec = 0.0f;
+          }
         }
       }
-    } else if (active) {
-      // ---- generic per-column march (learning frames, first tiles of a push, partial tiles, dense debug rows) ----
-      for (int f = 0; f < tf; ++f) {
-        const int t = t0 + f;
-        const float p = cur[f * width + tid];
-        const bool learning = a.noise_samples + t < a.learn_frames;
-        if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
-        const float q = noise_sub(p, thr, learning);
-        q_cur[f * width + tid] = q;  // a later steady tile looks back into this one
-        // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
-        float old;
-        if (t >= Y) {
-          float po;
-          if (ring_in_smem) {
-            po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
-          } else {
-            po = a.psd[static_cast<size_t>(t - Y) * n + j];
-          }
-          old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
+      __threadfence_block();
+      bar_arrive(kBarFull + (tile & 1), kDetectThreads);  // hand the averaged tile to the box warps
+      bar_sync(kBarMarch, kMarchThreads);                 // every march thread is done with tile-1's PSD buffer
+      issue_tile(tile + 2);                               // ... which tile+2 reuses
+    }
+    cp_async_wait<0>();
+    if (owner) {
+      a.threshold[j] = thr;
+      a.avg_sum[j] = sum;
+      a.avg_last[j] = last_avg;
+      // ring after the push, oldest -> newest: row i is in-push frame T - Y + i, or a surviving row of ring_in
+      for (int i = 0; i < Y; ++i) {
+        const int t = T - Y + i;
+        float q;
+        if (t >= 0) {
+          q = noise_sub(a.psd[static_cast<size_t>(t) * n + j], thr, a.noise_samples + t < a.learn_frames);
         } else {
-          old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
+          q = a.ring_in[static_cast<size_t>(T + i) * n + j];
         }
-        if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
-        const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
-        avg_tile[f * width + tid] = avg;
-        last_avg = avg;
-        if (owner) {
-          if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
-          if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
-          if (d == 1) {
-            spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
-            const int slot = slot_tile[f];
-            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-              spec = 0.0f;
+        a.ring_out[static_cast<size_t>(i) * n + j] = q;
+      }
+    }
+    if (spec_owner) a.spec_sum[j / d] = spec;
+  } else {
+    // ============================================ BOX warps ============================================
+    const int btid = tid - kMarchThreads;
+    constexpr int SEG = kBoxSegment;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int t0 = tile * kDetectTileFrames;
+      const int tf = min(kDetectTileFrames, T - t0);
+      bar_sync(kBarFull + (tile & 1), kDetectThreads);  // the march warps have written this average tile
+      const float* avg_tile = avg_tiles + (tile & 1) * tile_elems;
+      for (int item = btid; item < tf * (kDetectBinsPerCta / SEG); item += kBoxThreads) {
+        const int f = item / (kDetectBinsPerCta / SEG), b0 = (item - f * (kDetectBinsPerCta / SEG)) * SEG;
+        const int bin0 = j0 + b0;
+        if (bin0 >= n) continue;
+        const int t = t0 + f;
+        const float* row = avg_tile + f * width;
+        float box[SEG];
+        if (HALF_T > 0) {
+          constexpr int H = HALF_T > 0 ? HALF_T : 1;
+          float w[SEG + 2 * H];
+#pragma unroll
+          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];  // columns outside [0, N) hold 0.0f
+          boxcar_segment<H>(w, box);
+          if (segment_interior(bin0, n, half)) {
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) box[k] = div_const_fast<2 * H + 1>(box[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) box[k] = __fdiv_rn(box[k], static_cast<float>(boxcar_count(bin0 + k, n, half)));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) {
+            const int bin = bin0 + k;
+            box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return row[hp + (bb - j0)]; }, bin, n, half);
+          }
+        }
+        float top = box[0];
+#pragma unroll
+        for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
+        // watched keys: window maxima over ALL bins (also below the detection level), and the uncovered-candidate flag
+        if (rel_n > 0 || top >= a.start_level) {
+          const int gh = a.group_size / 2, margin = (a.group_size % 2 == 0) ? gh : gh + 1;
+          unsigned int covered = 0;  // bit k: bin0 + k lies inside some key's containsWithMargin interval
+          for (int r = 0; r < rel_n; ++r) {
+            const int key = rel_key[r], w = rel_slot[r];
+            if (bin0 + SEG - 1 >= key - gh && bin0 <= key + gh) {
+              float m = -INFINITY;
+#pragma unroll
+              for (int k = 0; k < SEG; ++k) {
+                const int bin = bin0 + k;
+                if (bin < n && bin >= key - gh && bin <= key + gh) m = fmaxf(m, box[k]);
+              }
+              if (m > -INFINITY) atomicMax(a.watch_max + static_cast<size_t>(t) * kMaxWatch + w, float_to_ordered(m));
+            }
+            if (bin0 + SEG - 1 >= key - margin && bin0 <= key + margin) {
+#pragma unroll
+              for (int k = 0; k < SEG; ++k) covered |= (bin0 + k >= key - margin && bin0 + k <= key + margin) ? (1u << k) : 0u;
             }
           }
+          if (top >= a.start_level) {
+            bool uncovered = false;
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) uncovered |= (bin0 + k < n) && box[k] >= a.start_level && !((covered >> k) & 1u);
+            if (uncovered) a.cand_flag[t] = 1;
+          }
         }
-      }
-      thr_s[tid] = thr;  // learning may have raised it
-    }
-    __syncthreads();
-    TK(2)
-    // ---- phase 2: boxcar + threshold over the tile's (frame, bin) grid; one work item = 8 consecutive bins ----
-    constexpr int SEG = kBoxSegment;
-    for (int item = tid; item < tf * (kDetectBinsPerCta / SEG); item += kDetectThreads) {
-      const int f = item / (kDetectBinsPerCta / SEG), b0 = (item - f * (kDetectBinsPerCta / SEG)) * SEG;
-      const int bin0 = j0 + b0;
-      if (bin0 >= n) continue;
-      const int t = t0 + f;
-      const float* row = avg_tile + f * width;
-      float box[SEG];
-      if (HALF_T > 0) {
-        constexpr int H = HALF_T > 0 ? HALF_T : 1;
-        float w[SEG + 2 * H];
-#pragma unroll
-        for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];  // columns outside [0, N) hold 0.0f
-        boxcar_segment<H>(w, box);
-        if (segment_interior(bin0, n, half)) {
-#pragma unroll
-          for (int k = 0; k < SEG; ++k) box[k] = div_const_fast<2 * H + 1>(box[k]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < SEG; ++k) box[k] = __fdiv_rn(box[k], static_cast<float>(boxcar_count(bin0 + k, n, half)));
-        }
-      } else {
+        if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {
           const int bin = bin0 + k;
-          box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return row[hp + (bb - j0)]; }, bin, n, half);
-        }
-      }
-      float top = box[0];
-#pragma unroll
-      for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
-      // watched keys: window maxima over ALL bins (also below the detection level), and the uncovered-candidate flag
-      if (a.n_watch > 0 || top >= a.start_level) {
-        const int gh = a.group_size / 2, margin = (a.group_size % 2 == 0) ? gh : gh + 1;
-        unsigned int covered = 0;  // bit k: bin0 + k lies inside some key's containsWithMargin interval
-        for (int w = 0; w < a.n_watch; ++w) {
-          const int key = a.watch_key[w];
-          if (bin0 + SEG - 1 >= key - gh && bin0 <= key + gh) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < SEG; ++k) {
-              const int bin = bin0 + k;
-              if (bin < n && bin >= key - gh && bin <= key + gh) m = fmaxf(m, box[k]);
+          if (bin < n) {
+            if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
+            if (box[k] >= a.detect_level) {
+              const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
+              stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
             }
-            if (m > -INFINITY) atomicMax(a.watch_max + static_cast<size_t>(t) * kMaxWatch + w, float_to_ordered(m));
-          }
-          if (bin0 + SEG - 1 >= key - margin && bin0 <= key + margin) {
-#pragma unroll
-            for (int k = 0; k < SEG; ++k) covered |= (bin0 + k >= key - margin && bin0 + k <= key + margin) ? (1u << k) : 0u;
-          }
-        }
-        if (top >= a.start_level) {
-          bool uncovered = false;
-#pragma unroll
-          for (int k = 0; k < SEG; ++k) uncovered |= (bin0 + k < n) && box[k] >= a.start_level && !((covered >> k) & 1u);
-          if (uncovered) a.cand_flag[t] = 1;
-        }
-      }
-      if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
-#pragma unroll
-      for (int k = 0; k < SEG; ++k) {
-        const int bin = bin0 + k;
-        if (bin < n) {
-          if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
-          if (box[k] >= a.detect_level) {
-            const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
-            stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
           }
         }
       }
-    }
-    if (spec_owner && d > 1) {
-      for (int f = 0; f < tf; ++f) {
-        float s = 0.0f;
-        for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + tid + i]);  // spectrogram.cpp:52-56
-        spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));               // spectrogram.cpp:57
-        const int slot = slot_tile[f];
-        if (slot >= 0) {
-          a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-          spec = 0.0f;
+      bar_arrive(kBarEmpty + (tile & 1), kDetectThreads);  // this average buffer may be overwritten (tile + 2)
+      bar_sync(kBarBox, kBoxThreads);                      // all entries of the tile are staged
+      // flush: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list
+      if (btid < tf) {
+        const int cnt = stage_count[btid];
+        stage_base[btid] = cnt > 0 ? atomicAdd(a.slot_count + t0 + btid, cnt) : 0;
+      }
+      bar_sync(kBarBox, kBoxThreads);
+      for (int f = btid >> 5; f < tf; f += kBoxThreads >> 5) {  // one warp per frame
+        const int cnt = stage_count[f], base = stage_base[f];
+        for (int i = btid & 31; i < cnt; i += 32) {
+          if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + f) * a.slot_capacity + base + i] = stage[f * kDetectBinsPerCta + i];
         }
+        __syncwarp();
+        if ((btid & 31) == 0) stage_count[f] = 0;
       }
-    }
-    __syncthreads();       // everyone is done with tile-1's buffer (ring look-back) and with avg_tile / slot_tile
-    TK(3)
-    issue_tile(tile + 2);  // reuses the buffer of tile-1
-    // flush the staged detection entries: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list
-    if (tid < tf) {
-      const int cnt = stage_count[tid];
-      stage_base[tid] = cnt > 0 ? atomicAdd(a.slot_count + t0 + tid, cnt) : 0;
-    }
-    __syncthreads();
-    for (int f = tid >> 5; f < tf; f += kDetectThreads >> 5) {  // one warp per frame
-      const int cnt = stage_count[f], base = stage_base[f];
-      for (int i = tid & 31; i < cnt; i += 32) {
-        if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + f) * a.slot_capacity + base + i] = stage[f * kDetectBinsPerCta + i];
-      }
-      __syncwarp();
-      if ((tid & 31) == 0) stage_count[f] = 0;  // re-armed for the next tile (phase 2 of which is two barriers away)
-    }
-    TK(4)
-  }
-  cp_async_wait<0>();
-#ifdef B2S_K2_TIMING
-  if ((tid == 0 || tid == 300) && (blockIdx.x % 32 == 3 || blockIdx.x == 83 || blockIdx.x == 0 || blockIdx.x == 127 || blockIdx.x == 24) && T > 1000) {
-    printf("cta %3d tid %3d per-tile cycles: wait %6lld | 1a %6lld | 1b %6lld | ph2 %6lld | flush %6lld\n", blockIdx.x, tid, tk[0] / n_tiles, tk[1] / n_tiles, tk[2] / n_tiles,
-           tk[3] / n_tiles, tk[4] / n_tiles);
-  }
-#endif
-
-  if (owner) {
-    a.threshold[j] = thr;
-    a.avg_sum[j] = sum;
-    a.avg_last[j] = last_avg;
-    // ring after the push, oldest -> newest: row i is in-push frame T - Y + i, or a surviving row of ring_in
-    for (int i = 0; i < Y; ++i) {
-      const int t = T - Y + i;
-      float q;
-      if (t >= 0) {
-        q = noise_sub(a.psd[static_cast<size_t>(t) * n + j], thr, a.noise_samples + t < a.learn_frames);
-      } else {
-        q = a.ring_in[static_cast<size_t>(T + i) * n + j];
-      }
-      a.ring_out[static_cast<size_t>(i) * n + j] = q;
+      bar_sync(kBarBox, kBoxThreads);  // staging area re-armed before the next tile's entries arrive
     }
   }
-  if (spec_owner) a.spec_sum[j / d] = spec;
 }
 
 // Exclusive prefix of min(slot_count[t], capacity) over the T frames (one CTA), then per-frame ordering of the slot
