@@ -23,7 +23,7 @@ namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
-constexpr int kDetectThreads = 512;
+constexpr int kDetectThreads = 192 + 512;  // 6 march warps + 16 box warps (one per 8-bin segment)
 constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
 constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
 constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
@@ -220,8 +220,13 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   const int tile_elems = kDetectTileFrames * width;
   float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width] raw PSD (cp.async target)
   float* q_tiles = psd_tiles + kDetectBuffers * tile_elems;         // [2][TF][width] noise-subtracted rows (current, previous)
-  float* avg_tiles = q_tiles + 2 * tile_elems;                      // [2][TF][width] averaged rows handed to the box warps
-  int* stage_count = reinterpret_cast<int*>(avg_tiles + 2 * tile_elems);  // [TF] detection entries staged per frame of the tile
+  // averaged values handed to the box warps, TRANSPOSED: [2][width][kAvgPitch] (column-major, pitch 33). The march thread of
+  // column c writes avg[c*33 + f] (lane stride 33: conflict-free); a box warp reads one column for 32 frames at once
+  // (lane = frame: consecutive words, conflict-free).
+  constexpr int kAvgPitch = kDetectTileFrames + 1;
+  const int avg_elems = width * kAvgPitch;
+  float* avg_tiles = q_tiles + 2 * tile_elems;
+  int* stage_count = reinterpret_cast<int*>(avg_tiles + 2 * avg_elems);  // [TF] detection entries staged per frame of the tile
   int* stage_base = stage_count + kDetectTileFrames;                // [TF] where this CTA's block starts in the frame's slot list
   DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_base + kDetectTileFrames);  // [TF][kDetectBinsPerCta]
   __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];    // watched keys that touch this CTA's bins
@@ -248,7 +253,10 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   }
   if (tid < kDetectTileFrames) stage_count[tid] = 0;
   if (tid < width && (col0 + tid < 0 || col0 + tid >= n)) {  // columns outside the row: the boxcar sees the zero-extended row
-    for (int f = 0; f < 2 * kDetectTileFrames; ++f) avg_tiles[f * width + tid] = 0.0f;
+    for (int f = 0; f < kAvgPitch; ++f) {
+      avg_tiles[tid * kAvgPitch + f] = 0.0f;
+      avg_tiles[avg_elems + tid * kAvgPitch + f] = 0.0f;
+    }
   }
   __syncthreads();
 
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
       float* __restrict__ q_cur = q_tiles + (tile & 1) * tile_elems;
       const float* __restrict__ q_prev = q_tiles + ((tile & 1) ^ 1) * tile_elems;
-      float* __restrict__ avg_tile = avg_tiles + (tile & 1) * tile_elems;
+      float* __restrict__ avg_col = avg_tiles + (tile & 1) * avg_elems + tid * kAvgPitch;  // my column of the transposed tile
       // planned spectrogram row inside this tile (at most the first one is handled by the fast path)
       while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
       const int emit_f = (d > 0 && next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf) ? a.emit_frame[next_emit] - t0 : -1;
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
             sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
             const float avg = full ? div_const_fast<YC>(sum) : kNoData;
-            avg_tile[f * width + tid] = avg;
+            avg_col[f] = avg;
             q_cur[f * width + tid] = q[f];  // the next tile looks back into this one
             if (f == TF - 1) last_avg = avg;
           }
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
           }
           if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
           const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
-          avg_tile[f * width + tid] = avg;
+          avg_col[f] = avg;
           last_avg = avg;
           if (owner) {
             if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
@@ -421,25 +429,25 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     if (spec_owner) a.spec_sum[j / d] = spec;
   } else {
     // ============================================ BOX warps ============================================
+    // warp w owns the 8-bin segment w of the CTA's 128 bins; lane = frame of the tile
     const int btid = tid - kMarchThreads;
+    const int lane = btid & 31, seg = btid >> 5;
     constexpr int SEG = kBoxSegment;
+    static_assert(kBoxThreads / 32 == kDetectBinsPerCta / kBoxSegment && kDetectTileFrames == 32, "one box warp per segment, one lane per frame");
+    const int b0 = seg * SEG, bin0 = j0 + b0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * kDetectTileFrames;
       const int tf = min(kDetectTileFrames, T - t0);
       bar_sync(kBarFull + (tile & 1), kDetectThreads);  // the march warps have written this average tile
-      const float* avg_tile = avg_tiles + (tile & 1) * tile_elems;
-      for (int item = btid; item < tf * (kDetectBinsPerCta / SEG); item += kBoxThreads) {
-        const int f = item / (kDetectBinsPerCta / SEG), b0 = (item - f * (kDetectBinsPerCta / SEG)) * SEG;
-        const int bin0 = j0 + b0;
-        if (bin0 >= n) continue;
-        const int t = t0 + f;
-        const float* row = avg_tile + f * width;
+      const float* avg_tile = avg_tiles + (tile & 1) * avg_elems;
+      const int f = lane, t = t0 + f;
+      if (f < tf && bin0 < n) {
         float box[SEG];
         if (HALF_T > 0) {
           constexpr int H = HALF_T > 0 ? HALF_T : 1;
           float w[SEG + 2 * H];
 #pragma unroll
-          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = row[hp + b0 - H + i];  // columns outside [0, N) hold 0.0f
+          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kAvgPitch + f];  // columns outside [0, N) hold 0.0f
           boxcar_segment<H>(w, box);
           if (segment_interior(bin0, n, half)) {
 #pragma unroll
@@ -452,7 +460,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
 #pragma unroll
           for (int k = 0; k < SEG; ++k) {
             const int bin = bin0 + k;
-            box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return row[hp + (bb - j0)]; }, bin, n, half);
+            box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return avg_tile[(hp + (bb - j0)) * kAvgPitch + f]; }, bin, n, half);
           }
         }
         float top = box[0];
@@ -485,15 +493,16 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             if (uncovered) a.cand_flag[t] = 1;
           }
         }
-        if (!a.dense_box && top < a.detect_level) continue;  // nothing to report from these 8 bins
+        if (a.dense_box || top >= a.detect_level) {
 #pragma unroll
-        for (int k = 0; k < SEG; ++k) {
-          const int bin = bin0 + k;
-          if (bin < n) {
-            if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
-            if (box[k] >= a.detect_level) {
-              const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
-              stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
+          for (int k = 0; k < SEG; ++k) {
+            const int bin = bin0 + k;
+            if (bin < n) {
+              if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
+              if (box[k] >= a.detect_level) {
+                const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
+                stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
+              }
             }
           }
         }
