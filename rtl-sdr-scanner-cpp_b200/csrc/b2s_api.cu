@@ -18,7 +18,7 @@
 #include "../../include/b2s.h"
 #include "detect.cuh"
 #include "host_utils.h"
-#include "spectral.cuh"
+#include "spectral2.cuh"
 #include "tracker.h"
 
 namespace {
@@ -129,9 +129,33 @@ int launch_spectrum_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t s
   CU(cudaGetLastError());
   return 0;
 }
+template <int N, int MODE, bool LIN>
+int launch_spectrum2_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+  using PL = FftPlanT<N>;
+  constexpr int T = N / PL::E;
+  const size_t smem = sizeof(float) * (2 * plane_elems<N>() + TwiddleLayout2<N>::SMEM) + (MODE == kModeCs8Tma ? 2 * N : 0);
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(k_spectrum2<N, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum2<N, MODE, LIN>, T, smem));
+    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum2<%d> does not fit on an SM", N);
+    configured = true;
+  }
+  const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
+  k_spectrum2<N, MODE, LIN><<<grid, T, smem, stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+constexpr bool use_packed_kernel(int n) { return n >= 4096; }  // the f32x2 variant needs 32 elements per thread
+
 template <int N, int MODE>
 int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   if (!a.peak_index || !a.peak_value) return fail(B2S_E_INVALID, "peak buffers are required");
+  if constexpr (use_packed_kernel(N)) {
+    if (a.power_lin) return launch_spectrum2_v<N, MODE, true>(e, a, stream);
+    return launch_spectrum2_v<N, MODE, false>(e, a, stream);
+  }
   // the |X|^2/fs debug rows exist only in the TMA instantiation's debug twin (parity tests); keep the others lean
   if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
   return launch_spectrum_v<N, MODE, false>(e, a, stream);
@@ -188,18 +212,30 @@ struct SpectralTables {
       // unpack scale folded into the window: x*scale*w -> x*(scale*w); differs from the two-step product by < 1 ulp
       for (int i = 0; i < n; ++i) w[i] = w[i] * cfg.iq_scale;
     }
-    // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)) in the order of TwiddleLayout<N>
+    // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)): interleaved (re, im) in the order of TwiddleLayout<N>
+    // for k_spectrum; planar (real plane, then imaginary plane, per pass) in the order of TwiddleLayout2<N> for k_spectrum2
     std::vector<float2> tw;
     int radix[4] = {0, 0, 0, 0};
     plan_radices(n, radix);
     int P = radix[0];
+    const bool planar = use_packed_kernel(n);
     for (int pass = 1; pass < 4 && radix[pass] > 1; ++pass) {
       const int R = radix[pass];
+      std::vector<float> pr, pi;
       for (int m = 1; m < R; ++m) {
         for (int k = 0; k < P; ++k) {
           const double ang = -2.0 * M_PI * (static_cast<double>(k) * m) / (static_cast<double>(P) * R);
-          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+          if (planar) {
+            pr.push_back(static_cast<float>(std::cos(ang)));
+            pi.push_back(static_cast<float>(std::sin(ang)));
+          } else {
+            tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+          }
         }
+      }
+      if (planar) {  // (R-1)*P is even, so the planes pack into float2 slots exactly
+        for (size_t i = 0; i + 1 < pr.size(); i += 2) tw.push_back(make_float2(pr[i], pr[i + 1]));
+        for (size_t i = 0; i + 1 < pi.size(); i += 2) tw.push_back(make_float2(pi[i], pi[i + 1]));
       }
       P *= R;
     }
