@@ -19,6 +19,7 @@
 #include "detect.cuh"
 #include "host_utils.h"
 #include "spectral2.cuh"
+#include "spectral3.cuh"
 #include "tracker.h"
 
 namespace {
@@ -147,18 +148,45 @@ int launch_spectrum2_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t 
   CU(cudaGetLastError());
   return 0;
 }
-constexpr bool use_packed_kernel(int n) { return n >= 4096; }  // the f32x2 variant needs 32 elements per thread
+template <int N, int MODE, bool LIN>
+int launch_spectrum3_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+  constexpr int RA = N / 1024, T = RA * 32;
+  const size_t smem = sizeof(float2) * (RA * kBlockPitch + 31 * 32) + (MODE == kModeCs8Tma ? 2 * N : 0);
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(k_spectrum3<RA, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum3<RA, MODE, LIN>, T, smem));
+    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum3<%d> does not fit on an SM", N);
+    configured = true;
+  }
+  const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
+  k_spectrum3<RA, MODE, LIN><<<grid, T, smem, stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// Which K1 serves which FFT size. 1 = k_spectrum (Stockham, two barriers per pass), 2 = k_spectrum2 (same structure,
+// packed f32x2 arithmetic; measured slower, kept for A/B builds with -DB2S_K1_LARGE=2), 3 = k_spectrum3 (warp-local).
+#ifndef B2S_K1_LARGE
+#define B2S_K1_LARGE 3
+#endif
+constexpr int k1_variant(int n) { return n >= 4096 ? B2S_K1_LARGE : 1; }
 
 template <int N, int MODE>
 int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   if (!a.peak_index || !a.peak_value) return fail(B2S_E_INVALID, "peak buffers are required");
-  if constexpr (use_packed_kernel(N)) {
+  // the |X|^2/fs debug rows come from a debug twin of each instantiation (parity tests); the product one stays lean
+  if constexpr (k1_variant(N) == 3) {
+    if (a.power_lin) return launch_spectrum3_v<N, MODE, true>(e, a, stream);
+    return launch_spectrum3_v<N, MODE, false>(e, a, stream);
+  } else if constexpr (k1_variant(N) == 2) {
     if (a.power_lin) return launch_spectrum2_v<N, MODE, true>(e, a, stream);
     return launch_spectrum2_v<N, MODE, false>(e, a, stream);
+  } else {
+    if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
+    return launch_spectrum_v<N, MODE, false>(e, a, stream);
   }
-  // the |X|^2/fs debug rows exist only in the TMA instantiation's debug twin (parity tests); keep the others lean
-  if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
-  return launch_spectrum_v<N, MODE, false>(e, a, stream);
 }
 
 template <int MODE>
@@ -212,32 +240,47 @@ struct SpectralTables {
       // unpack scale folded into the window: x*scale*w -> x*(scale*w); differs from the two-step product by < 1 ulp
       for (int i = 0; i < n; ++i) w[i] = w[i] * cfg.iq_scale;
     }
-    // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)): interleaved (re, im) in the order of TwiddleLayout<N>
-    // for k_spectrum; planar (real plane, then imaginary plane, per pass) in the order of TwiddleLayout2<N> for k_spectrum2
     std::vector<float2> tw;
-    int radix[4] = {0, 0, 0, 0};
-    plan_radices(n, radix);
-    int P = radix[0];
-    const bool planar = use_packed_kernel(n);
-    for (int pass = 1; pass < 4 && radix[pass] > 1; ++pass) {
-      const int R = radix[pass];
-      std::vector<float> pr, pi;
-      for (int m = 1; m < R; ++m) {
-        for (int k = 0; k < P; ++k) {
-          const double ang = -2.0 * M_PI * (static_cast<double>(k) * m) / (static_cast<double>(P) * R);
-          if (planar) {
-            pr.push_back(static_cast<float>(std::cos(ang)));
-            pi.push_back(static_cast<float>(std::sin(ang)));
-          } else {
-            tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+    if (k1_variant(n) == 3) {
+      // k_spectrum3 (TwiddleLayout3): pass A  W_N^(b*k0) as [k0-1][b], b < 1024;  pass B  W_1024^(n2*k1) as [k1-1][n2]
+      const int ra = n / 1024;
+      for (int k0 = 1; k0 < ra; ++k0)
+        for (int b = 0; b < 1024; ++b) {
+          const double ang = -2.0 * M_PI * (static_cast<double>(b) * k0) / n;
+          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+        }
+      for (int k1 = 1; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const double ang = -2.0 * M_PI * (static_cast<double>(n2) * k1) / 1024.0;
+          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+        }
+    } else {
+      // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)): interleaved (re, im) in the order of TwiddleLayout<N>
+      // for k_spectrum; planar (real plane, then imaginary plane, per pass) in the order of TwiddleLayout2<N> for k_spectrum2
+      int radix[4] = {0, 0, 0, 0};
+      plan_radices(n, radix);
+      int P = radix[0];
+      const bool planar = k1_variant(n) == 2;
+      for (int pass = 1; pass < 4 && radix[pass] > 1; ++pass) {
+        const int R = radix[pass];
+        std::vector<float> pr, pi;
+        for (int m = 1; m < R; ++m) {
+          for (int k = 0; k < P; ++k) {
+            const double ang = -2.0 * M_PI * (static_cast<double>(k) * m) / (static_cast<double>(P) * R);
+            if (planar) {
+              pr.push_back(static_cast<float>(std::cos(ang)));
+              pi.push_back(static_cast<float>(std::sin(ang)));
+            } else {
+              tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
+            }
           }
         }
+        if (planar) {  // (R-1)*P is even, so the planes pack into float2 slots exactly
+          for (size_t i = 0; i + 1 < pr.size(); i += 2) tw.push_back(make_float2(pr[i], pr[i + 1]));
+          for (size_t i = 0; i + 1 < pi.size(); i += 2) tw.push_back(make_float2(pi[i], pi[i + 1]));
+        }
+        P *= R;
       }
-      if (planar) {  // (R-1)*P is even, so the planes pack into float2 slots exactly
-        for (size_t i = 0; i + 1 < pr.size(); i += 2) tw.push_back(make_float2(pr[i], pr[i + 1]));
-        for (size_t i = 0; i + 1 < pi.size(); i += 2) tw.push_back(make_float2(pi[i], pi[i + 1]));
-      }
-      P *= R;
     }
     int rc = wscale.alloc(n);
     if (rc) return rc;

@@ -1,0 +1,229 @@
+// K1, warp-local variant for N = RA * 1024 (RA = 4, 8, 16  ->  N = 4096, 8192, 16384).
+//
+// Same math as k_spectrum (spectral.cuh) — unpack, window, N-point forward FFT, fftshift, |X|^2/fs, dB, first maximum —
+// but organised so that the shared-memory pipe and the FP32 pipe overlap instead of alternating:
+//
+//   pass A  (block-wide)  radix-RA decimation in frequency over n0 (stride 1024), fed straight from the TMA-staged int8
+//                         frame, twiddled by W_N^(b*k0) (coalesced 8-byte loads from an L2-resident table) and written
+//                         to block k0 of the exchange buffer.                                   -> ONE block barrier
+//   pass B  (warp-local)  warp k0 owns block k0 (1024 points): radix-32 over n1 (stride 32), twiddle W_1024^(n2*k1) from
+//                         a small shared table, written back TRANSPOSED with pitch 33 inside the warp's own block.
+//   pass C  (warp-local)  radix-32 over n2 (now stride 33 -> conflict-free), no twiddles; lane k1 ends up holding bins
+//                         k0 + RA*k1 + 32*RA*k2. dB values go back into the warp's block ([k2][k1], skewed per block).
+//                                                                                              -> ONE block barrier
+//   output  (block-wide)  every thread gathers 4 consecutive bins (conflict-free thanks to the skew) and issues 16-byte
+//                         coalesced stores; row maximum / first index reduction.
+//
+// k_spectrum needs two barriers per pass (read-all / write-all of one shared buffer) which keeps all 16 warps in the same
+// phase: the LSU pipe idles while everybody computes and the FP32 pipe idles while everybody loads (profiles/
+// r01_k1_v1.1_ncu_summary.txt: LSU 52 %, issue 49 %). Here passes B and C only need __syncwarp, so warps drift apart
+// and one warp's loads overlap another warp's butterflies.
+#pragma once
+#include "spectral.cuh"
+
+namespace b2s {
+
+// multiply by W32^j = exp(-2 pi i j / 32), j a compile-time constant after unrolling
+__device__ __forceinline__ float2 mul_w32(float2 a, int j) {
+  constexpr float C1 = 0.98078528040323043f, S1 = 0.19509032201612825f;  // pi/16
+  constexpr float C2 = 0.92387953251128674f, S2 = 0.38268343236508977f;  // 2pi/16
+  constexpr float C3 = 0.83146961230254524f, S3 = 0.55557023301960218f;  // 3pi/16
+  constexpr float H = 0.70710678118654752f;                               // 4pi/16
+  switch (j & 31) {
+    case 0: return a;
+    case 8: return mul_mi(a);
+    case 16: return make_float2(-a.x, -a.y);
+    case 24: return make_float2(-a.y, a.x);
+    case 1: return cmul(a, make_float2(C1, -S1));
+    case 2: return cmul(a, make_float2(C2, -S2));
+    case 3: return cmul(a, make_float2(C3, -S3));
+    case 4: return cmul(a, make_float2(H, -H));
+    case 5: return cmul(a, make_float2(S3, -C3));
+    case 6: return cmul(a, make_float2(S2, -C2));
+    case 7: return cmul(a, make_float2(S1, -C1));
+    case 9: return cmul(a, make_float2(-S1, -C1));
+    case 10: return cmul(a, make_float2(-S2, -C2));
+    case 11: return cmul(a, make_float2(-S3, -C3));
+    case 12: return cmul(a, make_float2(-H, -H));
+    case 13: return cmul(a, make_float2(-C3, -S3));
+    case 14: return cmul(a, make_float2(-C2, -S2));
+    case 15: return cmul(a, make_float2(-C1, -S1));
+    case 17: return cmul(a, make_float2(-C1, S1));
+    case 18: return cmul(a, make_float2(-C2, S2));
+    case 19: return cmul(a, make_float2(-C3, S3));
+    case 20: return cmul(a, make_float2(-H, H));
+    case 21: return cmul(a, make_float2(-S3, C3));
+    default: return cmul(a, make_float2(C1, S1));  // not reached: n2*k1 <= 21 in the 4x8 split
+  }
+}
+
+// 32-point DFT in registers: Cooley-Tukey 4 x 8 (n = 8*n1 + n2, k = k1 + 4*k2)
+__device__ __forceinline__ void dft32(float2* v) {
+  float2 y[8][4];
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2) {
+    float2 a[4];
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) a[n1] = v[8 * n1 + n2];
+    Dft<4>::run(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) y[n2][k1] = mul_w32(a[k1], n2 * k1);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    float2 b[8];
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) b[n2] = y[n2][k1];
+    Dft<8>::run(b);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) v[k1 + 4 * k2] = b[k2];
+  }
+}
+
+constexpr int kBlockPitch = 32 * 33;  // float2 elements per warp-owned block (32 rows of pitch 33 after pass B)
+
+// twiddle tables for this kernel (host builds them in this order, all float2):
+//   [0, (RA-1)*1024)            pass A: W_N^(b*k0), laid out [k0-1][b]
+//   [(RA-1)*1024, +31*32)       pass B: W_1024^(n2*k1), laid out [k1-1][n2]
+template <int RA>
+struct TwiddleLayout3 {
+  static constexpr int A = (RA - 1) * 1024, B = 31 * 32, TOTAL = A + B;
+};
+
+template <int RA, int MODE, bool DEBUG_LIN>
+__global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
+  constexpr int N = RA * 1024, T = RA * 32, BPT = 32 / RA;  // threads, pass-A butterflies per thread
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* X = reinterpret_cast<float2*>(smem);                                 // [RA][kBlockPitch]
+  float2* twB = X + RA * kBlockPitch;                                          // [31][32]
+  unsigned char* raw = reinterpret_cast<unsigned char*>(twB + 31 * 32);        // 2N bytes (TMA mode only)
+  float* Xf = reinterpret_cast<float*>(X);
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ float red_v[32];
+  __shared__ int red_i[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const char* base = static_cast<const char*>(a.iq);
+  const float2* twA = a.twiddle;
+
+  if (MODE == kModeCs8Tma && tid == 0) {
+    mbar_init(&full_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 31 * 32; i += T) twB[i] = a.twiddle[TwiddleLayout3<RA>::A + i];
+  __syncthreads();
+  if (MODE == kModeCs8Tma && tid == 0 && static_cast<int>(blockIdx.x) < a.n_frames) {
+    mbar_arrive_expect_tx(&full_bar, 2 * N);
+    bulk_g2s(raw, base + static_cast<long long>(blockIdx.x) * a.frame_stride_bytes, 2 * N, &full_bar);
+  }
+
+  uint32_t parity = 0;
+  for (int frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+    // ---------------- pass A: radix RA over n0 (stride 1024), input = windowed int8 samples ----------------
+    if (MODE == kModeCs8Tma) mbar_wait(&full_bar, parity);
+    parity ^= 1;
+#pragma unroll
+    for (int u = 0; u < BPT; ++u) {
+      const int b = tid + u * T;  // 0..1023
+      float2 v[RA];
+#pragma unroll
+      for (int m = 0; m < RA; ++m) {
+        const int n = m * 1024 + b;
+        const float w = __ldg(&a.wscale[n]);
+        if (MODE == kModeCs8Tma) {
+          const char2 s = reinterpret_cast<const char2*>(raw)[n];
+          v[m] = make_float2(static_cast<float>(s.x) * w, static_cast<float>(s.y) * w);
+        } else if (MODE == kModeCs8Direct) {
+          const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+          v[m] = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+        } else {
+          const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+          v[m] = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+        }
+      }
+      Dft<RA>::run(v);
+      X[b] = v[0];
+#pragma unroll
+      for (int k0 = 1; k0 < RA; ++k0) X[k0 * kBlockPitch + b] = cmul(v[k0], __ldg(&twA[(k0 - 1) * 1024 + b]));
+    }
+    __syncthreads();
+    if (MODE == kModeCs8Tma && tid == 0) {  // staging buffer consumed: fetch this CTA's next frame behind the remaining passes
+      const int next = frame + gridDim.x;
+      if (next < a.n_frames) {
+        mbar_arrive_expect_tx(&full_bar, 2 * N);
+        bulk_g2s(raw, base + static_cast<long long>(next) * a.frame_stride_bytes, 2 * N, &full_bar);
+      }
+    }
+    // ---------------- passes B and C: warp `warp` owns block k0 = warp ----------------
+    float2 v[32];
+    float2* blk = X + warp * kBlockPitch;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) v[m] = blk[m * 32 + lane];  // element (n1 = m, n2 = lane)
+    __syncwarp();                                             // every lane has its inputs before anyone overwrites the block
+    dft32(v);
+    blk[lane * 33] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) blk[lane * 33 + k1] = cmul(v[k1], twB[(k1 - 1) * 32 + lane]);  // transposed: [n2][k1], pitch 33
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 32; ++m) v[m] = blk[m * 33 + lane];  // element (k1 = lane, n2 = m)
+    __syncwarp();
+    dft32(v);
+    // lane k1 holds X[k0 + RA*k1 + 32*RA*k2] in v[k2]: |X|^2/fs -> dB (psd.cpp:18), parked in the warp's block as [k2][k1]
+    float best_v = -INFINITY;
+    float* res = Xf + warp * (2 * kBlockPitch) + 2 * warp;  // skew of 2 floats per block keeps the gather below conflict-free
+    constexpr float kDbPerLog2 = 3.0102999566398120f;
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+      const float pw = fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y) * a.inv_fs;
+      const float db = kDbPerLog2 * fast_log2(pw);
+      res[k2 * 32 + lane] = DEBUG_LIN ? pw : db;
+      if (DEBUG_LIN) v[k2].x = db;
+      best_v = fmaxf(best_v, db);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best_v = fmaxf(best_v, __shfl_xor_sync(0xffffffffu, best_v, o));
+    if (lane == 0) red_v[warp] = best_v;
+    if (tid == 0) red_i[0] = 0x7fffffff;
+    __syncthreads();
+    // ---------------- output: 4 consecutive bins per thread, 16-byte coalesced stores at (bin + N/2) mod N ----------------
+    float row_max = red_v[0];
+#pragma unroll
+    for (int w = 1; w < RA; ++w) row_max = fmaxf(row_max, red_v[w]);
+    float* row = a.psd_db + static_cast<size_t>(frame) * N;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < N / (4 * T); ++i) {
+      const int bin = 4 * (tid + i * T);
+      const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
+      const int k0 = bin & (RA - 1);
+      float4 o;
+      const float* src = Xf + k2 * 32 + k1;
+      o.x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
+      o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
+      o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
+      o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
+      const int j = (bin + N / 2) & (N - 1);
+      if (DEBUG_LIN) {  // debug instantiation: the block holds |X|^2/fs; dB is recomputed here
+        *reinterpret_cast<float4*>(a.power_lin + static_cast<size_t>(frame) * N + j) = o;
+        o.x = kDbPerLog2 * fast_log2(o.x);
+        o.y = kDbPerLog2 * fast_log2(o.y);
+        o.z = kDbPerLog2 * fast_log2(o.z);
+        o.w = kDbPerLog2 * fast_log2(o.w);
+      }
+      *reinterpret_cast<float4*>(row + j) = o;
+      if (o.x == row_max) best_i = min(best_i, j);
+      if (o.y == row_max) best_i = min(best_i, j + 1);
+      if (o.z == row_max) best_i = min(best_i, j + 2);
+      if (o.w == row_max) best_i = min(best_i, j + 3);
+    }
+    if (best_i != 0x7fffffff) atomicMin(&red_i[0], best_i);
+    __syncthreads();  // the exchange buffer is free again; red_i is final
+    if (tid == 0) {
+      a.peak_index[frame] = red_i[0];
+      a.peak_value[frame] = row_max;
+    }
+  }
+}
+
+}  // namespace b2s
