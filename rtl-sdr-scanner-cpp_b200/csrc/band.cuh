@@ -552,8 +552,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * ((kDetectBuffers + 2) * kDetectTileFrames * width + 2 * width * (kDetectTileFrames + 1)) +
-                        sizeof(int) * 2 * kDetectTileFrames + sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta;
+    const size_t smem = sizeof(float) * (kDetectBuffers * kDetectTileFrames * width + 2 * width * (kDetectTileFrames + 1)) +
+                        2 * (sizeof(int) * kDetectTileFrames + sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta);
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {

@@ -23,8 +23,7 @@ namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
-constexpr int kDetectThreads = 192 + 512;  // 6 march warps + 16 box warps (one per 8-bin segment)
-constexpr int kDetectBuffers = 3;       // PSD tiles resident: current, previous (ring look-back), next (in flight)
+constexpr int kDetectBuffers = 3;       // PSD tiles resident in the shared ring (being consumed / landed / in flight)
 constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
 constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
@@ -178,65 +177,76 @@ __device__ __forceinline__ float boxcar_value(At at, int j, int n, int half) {
   return __fdiv_rn(s, static_cast<float>(boxcar_count(j, n, half)));
 }
 
-// 16-byte asynchronous global->shared copy (LDGSTS); used to stream PSD tiles ahead of the march
+// 16-byte asynchronous global->shared copy (LDGSTS) and its completion hook on an mbarrier
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// One CTA owns kDetectBinsPerCta bins plus a halo of X/2 bins (rounded up to 4) on each side, computed redundantly.
-// PSD tiles of kDetectTileFrames rows are streamed into shared memory with cp.async two tiles ahead; one thread per
-// column marches the tile through noise -> Averager (the only serial chain: two dependent FADDs per frame); then all
-// threads evaluate boxcar + threshold for the tile's (frame, bin) grid.
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#ifndef B2S_K2_BULK_ROWS
+#define B2S_K2_BULK_ROWS 1  // 1: one cp.async.bulk per row (one instruction per lane and tile); 0: LDGSTS chunks (the issue loop alone costs ~10k cycles per tile)
+#endif
 // named barriers (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-constexpr int kMarchThreads = 192;                              // warps 0-5: one thread per column (<= 192 columns)
-constexpr int kBoxThreads = kDetectThreads - kMarchThreads;     // warps 6-15: boxcar + threshold + emission
-constexpr int kBarMarch = 1, kBarBox = 2, kBarFull = 3 /*,4*/, kBarEmpty = 5 /*,6*/;
+// Warp roles of k_detect. One CTA owns kDetectBinsPerCta bins plus a halo of X/2 bins (rounded up to 4) on each side,
+// computed redundantly; every role walks the push in tiles of kDetectTileFrames frames and the roles meet only through
+// mbarriers, so each runs as far ahead as its buffers allow.
+constexpr int kSumWarps = 6, kSpecWarps = 4, kBoxWarps = kDetectBinsPerCta / 8;
+constexpr int kSumThreads = 32 * kSumWarps;    // one thread per column (<= 192 columns)
+constexpr int kSpecThreads = 32 * kSpecWarps;  // one thread per owned bin
+constexpr int kBoxThreads = 32 * kBoxWarps;    // one warp per 8-bin segment, lane = frame of the tile
+constexpr int kDetectThreads = kSumThreads + kSpecThreads + 32 /*producer*/ + 32 /*flush*/ + kBoxThreads;
+constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/, kBarStageFull = 6 /*,7*/, kBarStageEmpty = 8 /*,9*/;  // hardware barriers: waiting warps sleep instead of polling
 
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
 // or 0 / -1 for the generic runtime-parameter instantiation.
 //
-// Warp-specialised, software-pipelined over tiles of 32 frames:
-//   MARCH warps (one thread per column): stream the PSD tile in with cp.async, NoiseLearner subtraction, the serial
-//     Averager chain (m_sum -= leaving; m_sum += entering; m_average = m_sum / Y), spectrogram accumulation; they write the
-//     tile of averaged values into one of two shared buffers and move on to the next tile.
-//   BOX warps: boxcar over 8-bin segments + threshold + watched-window maxima for the tile the march warps finished one
-//     step earlier; detection entries are staged in shared memory and flushed with one global atomic per (CTA, frame).
-// The two groups meet only through FULL/EMPTY named barriers on the double-buffered average tile, so the serial chain of
-// tile i+1 overlaps the throughput work of tile i. Steady-state tiles (no learning frame, ring look-back inside the push,
-// full tile, no dense debug rows) take a branch-free register-resident march; all others a generic per-column march with
-// the same float operations in the same order (bit-identical, tested).
+//   PRODUCER warp  streams PSD tiles [32 frames][width] into a 3-deep shared ring: one cp.async.bulk per row (lane = row),
+//                  completion counted on an mbarrier (p_full), slots recycled through p_empty.
+//   SUM warps      (thread = column) the only truly serial chain of the path: NoiseLearner subtraction and
+//                  m_sum -= leaving; m_sum += entering (averager.cpp:40-50), two dependent FADDs per frame. Nothing
+//                  else lives on this instruction stream: the last Y noise-subtracted values stay in registers from tile to
+//                  tile, and the running sums go to a transposed shared tile (s_full / s_empty).
+//   SPEC warps     (thread = owned bin) Spectrogram::process: the second serial chain (accumulation of raw rows).
+//   BOX warps      (warp = 8-bin segment, lane = frame) m_average = m_sum / Y for the 8 + 2H columns of the segment, boxcar,
+//                  threshold, watched-window maxima; detection entries are staged in shared memory and flushed with one
+//                  global atomic per (CTA, frame).
+// Steady-state tiles (no learning frame, ring look-back inside the push, full tile, no dense debug rows) take a
+// register-resident fully unrolled march; all others a generic one with the same float operations in the same order
+// (bit-identical, tested).
 template <int Y_T, int HALF_T>
 __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
+  constexpr int TF = kDetectTileFrames;
+  static_assert(Y_T <= TF, "the register-resident ring look-back needs Y <= tile frames");
   const int half = HALF_T >= 0 ? HALF_T : a.group_x / 2;
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
-  const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA (<= kMarchThreads)
-  const int tile_elems = kDetectTileFrames * width;
-  float* psd_tiles = sm;                                            // [kDetectBuffers][TF][width] raw PSD (cp.async target)
-  float* q_tiles = psd_tiles + kDetectBuffers * tile_elems;         // [2][TF][width] noise-subtracted rows (current, previous)
-  // averaged values handed to the box warps, TRANSPOSED: [2][width][kAvgPitch] (column-major, pitch 33). The march thread of
-  // column c writes avg[c*33 + f] (lane stride 33: conflict-free); a box warp reads one column for 32 frames at once
-  // (lane = frame: consecutive words, conflict-free).
-  constexpr int kAvgPitch = kDetectTileFrames + 1;
-  const int avg_elems = width * kAvgPitch;
-  float* avg_tiles = q_tiles + 2 * tile_elems;
-  int* stage_count = reinterpret_cast<int*>(avg_tiles + 2 * avg_elems);  // [TF] detection entries staged per frame of the tile
-  int* stage_base = stage_count + kDetectTileFrames;                // [TF] where this CTA's block starts in the frame's slot list
-  DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_base + kDetectTileFrames);  // [TF][kDetectBinsPerCta]
-  __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];    // watched keys that touch this CTA's bins
+  const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA (<= kSumThreads)
+  const int tile_elems = TF * width;
+  float* psd_tiles = sm;                            // [kDetectBuffers][TF][width] raw PSD rows (bulk-copy target)
+  // averaged values (m_average) handed to the box warps, TRANSPOSED: [2][width][kSumPitch] (column-major, pitch 33). The
+  // SUM thread of column c writes avg[c*33 + f] (lane stride 33: conflict-free); a box warp reads one column for 32
+  // frames at once (lane = frame: consecutive words, conflict-free).
+  constexpr int kSumPitch = TF + 1;
+  const int sum_elems = width * kSumPitch;
+  float* sum_tiles = psd_tiles + kDetectBuffers * tile_elems;
+  int* stage_count = reinterpret_cast<int*>(sum_tiles + 2 * sum_elems);  // [2][TF] detection entries staged per frame of the tile
+  DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_count + 2 * TF);  // [2][TF][kDetectBinsPerCta]
+  __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];          // watched keys that touch this CTA's bins
+  __shared__ __align__(8) uint64_t p_full[kDetectBuffers], p_empty[kDetectBuffers];
 
   const int n = a.n, T = a.n_frames, Y = Y_T > 0 ? Y_T : a.group_y;
   const int j0 = blockIdx.x * kDetectBinsPerCta;
   const int col0 = j0 - hp;  // bin of column 0
   const int tid = threadIdx.x;
-  const int n_tiles = (T + kDetectTileFrames - 1) / kDetectTileFrames;
+  const int n_tiles = (T + TF - 1) / TF;
   const bool dense = a.dense_q || a.dense_avg || a.dense_box;
+  const float* __restrict__ psd = a.psd;
+  const float* __restrict__ ring_in = a.ring_in;
 
   // ---- one-time setup (all threads) ----
   if (tid == 0) {
@@ -250,95 +260,60 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       }
     }
     rel_n = cnt;
+    for (int i = 0; i < kDetectBuffers; ++i) {
+      mbar_init(&p_full[i], B2S_K2_BULK_ROWS ? 1 : 32);
+      mbar_init(&p_empty[i], kSumWarps + kSpecWarps);
+    }
+    fence_barrier_init();
   }
-  if (tid < kDetectTileFrames) stage_count[tid] = 0;
+  if (tid < 2 * TF) stage_count[tid] = 0;
   if (tid < width && (col0 + tid < 0 || col0 + tid >= n)) {  // columns outside the row: the boxcar sees the zero-extended row
-    for (int f = 0; f < kAvgPitch; ++f) {
-      avg_tiles[tid * kAvgPitch + f] = 0.0f;
-      avg_tiles[avg_elems + tid * kAvgPitch + f] = 0.0f;
+    for (int f = 0; f < kSumPitch; ++f) {
+      sum_tiles[tid * kSumPitch + f] = 0.0f;
+      sum_tiles[sum_elems + tid * kSumPitch + f] = 0.0f;
     }
   }
   __syncthreads();
 
-  if (tid < kMarchThreads) {
-    // =========================================== MARCH warps ===========================================
+  const int lane = tid & 31;
+  if (tid < kSumThreads) {
+    // ============================================ SUM warps ============================================
     const int j = col0 + tid;  // my column's bin
     const bool active = tid < width && j >= 0 && j < n;
     const bool owner = active && tid >= hp && tid < hp + kDetectBinsPerCta;
-    const int chunks_per_row = width / 4;
-    auto issue_tile = [&](int tile) {
-      if (tile < n_tiles) {
-        float* dst = psd_tiles + (tile % kDetectBuffers) * tile_elems;
-        const int t_base = tile * kDetectTileFrames;
-        for (int c = tid; c < kDetectTileFrames * chunks_per_row; c += kMarchThreads) {
-          const int f = c / chunks_per_row, x = (c - f * chunks_per_row) * 4;
-          const int t = t_base + f, col = col0 + x;
-          if (t < T && col >= 0 && col + 3 < n) cp_async16(dst + f * width + x, a.psd + static_cast<size_t>(t) * n + col);
-        }
-      }
-      cp_async_commit();
-    };
     float thr = active ? a.threshold[j] : 0.0f;
     float sum = active ? a.avg_sum[j] : 0.0f;
-    float last_avg = kNoData;
-    const int d = a.spec_out > 0 ? n / a.spec_out : 0;
-    const bool spec_owner = owner && d > 0 && (j % d) == 0;
-    float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
-    const bool ring_in_smem = Y <= kDetectTileFrames;
-    int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
+    constexpr int YC = Y_T > 0 ? Y_T : 1;
+    float lead[YC];  // noise-subtracted values of the last Y frames of the previous tile (the rows about to leave the ring)
+#pragma unroll
+    for (int f = 0; f < YC; ++f) lead[f] = 0.0f;
+    bool lead_valid = false;
 
-    issue_tile(0);
-    issue_tile(1);
     for (int tile = 0; tile < n_tiles; ++tile) {
-      const int t0 = tile * kDetectTileFrames;
-      const int tf = min(kDetectTileFrames, T - t0);
-      cp_async_wait<1>();                     // my part of tile `tile` has landed (tile+1 may still be in flight)
-      bar_sync(kBarMarch, kMarchThreads);     // ... and everybody else's part; also: tile-1 is fully consumed
-      if (tile >= 2) bar_sync(kBarEmpty + (tile & 1), kDetectThreads);  // the box warps are done with this average buffer
-      const float* __restrict__ cur = psd_tiles + (tile % kDetectBuffers) * tile_elems;
-      const float* __restrict__ prev = psd_tiles + ((tile + kDetectBuffers - 1) % kDetectBuffers) * tile_elems;
-      float* __restrict__ q_cur = q_tiles + (tile & 1) * tile_elems;
-      const float* __restrict__ q_prev = q_tiles + ((tile & 1) ^ 1) * tile_elems;
-      float* __restrict__ avg_col = avg_tiles + (tile & 1) * avg_elems + tid * kAvgPitch;  // my column of the transposed tile
-      // planned spectrogram row inside this tile (at most the first one is handled by the fast path)
-      while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-      const int emit_f = (d > 0 && next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf) ? a.emit_frame[next_emit] - t0 : -1;
-      auto slot_of = [&](int f) {  // planned row emitted after frame t0 + f, or -1
-        int slot = -1;
-        for (int i = next_emit; i < a.n_emit && a.emit_frame[i] <= t0 + f; ++i) slot = (a.emit_frame[i] == t0 + f) ? i : slot;
-        return slot;
-      };
-      // steady state: whole tile, ring look-back inside the push, no learning frame in the tile
-      // (the look-back reads q_prev, which every earlier tile wrote — learning frames as -100 — whichever path it took)
-      const bool steady = Y_T > 0 && HALF_T > 0 && tf == kDetectTileFrames && t0 >= kDetectTileFrames && Y <= kDetectTileFrames &&
-                          (a.noise_samples + t0 >= a.learn_frames) && !dense;
+      const int t0 = tile * TF;
+      const int tf = min(TF, T - t0);
+      const int ps = tile % kDetectBuffers, sb = tile & 1;
+      const float* __restrict__ cur = psd_tiles + ps * tile_elems + tid;
+      float* __restrict__ sum_col = sum_tiles + sb * sum_elems + tid * kSumPitch;  // my column of the transposed tile
+      const bool steady = Y_T > 0 && tf == TF && t0 >= Y && lead_valid && (a.noise_samples + t0 >= a.learn_frames) && !dense;
+      // frames leaving the ring that neither this tile nor `lead` holds: fetched before anything waits (one latency)
+      float oldraw[TF];
+      if (!steady && active) {
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+          const int t = t0 + f;
+          oldraw[f] = 0.0f;
+          if (f < tf && (f < Y || t < Y)) oldraw[f] = (t < Y) ? ring_in[static_cast<size_t>(t) * n + j] : psd[static_cast<size_t>(t - Y) * n + j];
+        }
+      }
+      mbar_wait_sleepy(&p_full[ps], (tile / kDetectBuffers) & 1);        // the PSD tile has landed
+      if (tile >= 2) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this sum buffer
+      float q[TF];
       if (steady) {
         if (active) {
           if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
-          constexpr int YC = Y_T > 0 ? Y_T : 1;
-          constexpr int TF = kDetectTileFrames;
-          const bool full = a.avg_frames + t0 + 1 >= YC;  // m_frames has reached groupSize
-          float q[TF], lead[YC];
 #pragma unroll
-          for (int f = 0; f < TF; ++f) q[f] = cur[f * width + tid];
-#pragma unroll
-          for (int f = 0; f < YC; ++f) lead[f] = q_prev[(f - YC + TF) * width + tid];  // rows leaving the ring during the first Y frames
-          // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49)
-          if (d == 1 && owner) {
-            if (emit_f < 0) {
-#pragma unroll
-              for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, q[f]);
-            } else {
-              for (int f = 0; f < TF; ++f) {
-                spec = __fadd_rn(spec, cur[f * width + tid]);
-                const int slot = slot_of(f);
-                if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-                  a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-                  spec = 0.0f;
-                }
-              }
-            }
-          }
+          for (int f = 0; f < TF; ++f) q[f] = cur[f * width];
 #pragma unroll
           for (int f = 0; f < TF; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
 #pragma unroll
@@ -346,113 +321,188 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             const float old = (f >= YC) ? q[f - YC] : lead[f];
             sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
             sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
-            const float avg = full ? div_const_fast<YC>(sum) : kNoData;
-            avg_col[f] = avg;
-            q_cur[f * width + tid] = q[f];  // the next tile looks back into this one
-            if (f == TF - 1) last_avg = avg;
+            sum_col[f] = div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
           }
         }
       } else if (active) {
-        // ---- generic per-column march (learning frames, first tile of a push, partial tiles, dense debug rows) ----
-        for (int f = 0; f < tf; ++f) {
-          const int t = t0 + f;
-          const float p = cur[f * width + tid];
-          const bool learning = a.noise_samples + t < a.learn_frames;
-          if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
-          const float q = noise_sub(p, thr, learning);
-          q_cur[f * width + tid] = q;  // a later steady tile looks back into this one
-          // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
-          float old;
-          if (t >= Y) {
-            float po;
-            if (ring_in_smem) {
-              po = (f >= Y) ? cur[(f - Y) * width + tid] : prev[(f - Y + kDetectTileFrames) * width + tid];
+        // ---- generic march (learning frames, first tile of a push, partial tiles, dense debug rows, runtime Y) ----
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+          q[f] = 0.0f;
+          if (f < tf) {
+            const int t = t0 + f;
+            const float p = cur[f * width];
+            const bool learning = a.noise_samples + t < a.learn_frames;
+            if (learning) thr = fmaxf(thr, p);  // Noise::add, noise_learner.cpp:19-21
+            q[f] = noise_sub(p, thr, learning);
+            // value leaving the ring (frame t - Y): thr is final for every frame that was not a learning frame
+            float old;
+            if (t < Y) {
+              old = oldraw[f];  // the t-th oldest row of the pre-push ring
             } else {
-              po = a.psd[static_cast<size_t>(t - Y) * n + j];
+              const float po = (f >= Y) ? cur[(f - Y) * width] : oldraw[f];
+              old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
             }
-            old = noise_sub(po, thr, a.noise_samples + (t - Y) < a.learn_frames);
-          } else {
-            old = a.ring_in[static_cast<size_t>(t) * n + j];  // the t-th oldest row of the pre-push ring
-          }
-          if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
-          const float avg = averager_step(sum, old, q, min(a.avg_frames + t + 1, Y), Y);
-          avg_col[f] = avg;
-          last_avg = avg;
-          if (owner) {
-            if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q;
-            if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
-            if (d == 1) {
-              spec = __fadd_rn(spec, p);  // Spectrogram::process, spectrogram.cpp:46-49
-              const int slot = emit_f >= 0 ? slot_of(f) : -1;
-              if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72
-                a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-                spec = 0.0f;
-              }
+            if (owner && (t % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t
+            const float avg = averager_step(sum, old, q[f], min(a.avg_frames + t + 1, Y), Y);
+            sum_col[f] = avg;
+            if (owner) {
+              if (a.dense_q) a.dense_q[static_cast<size_t>(t) * n + j] = q[f];
+              if (a.dense_avg) a.dense_avg[static_cast<size_t>(t) * n + j] = avg;
             }
-          }
-        }
-      }
-      if (spec_owner && d > 1) {  // decimating spectrogram: mean of d adjacent raw bins, then accumulate (spectrogram.cpp:50-58)
-        for (int f = 0; f < tf; ++f) {
-          float s = 0.0f;
-          for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + tid + i]);
-          spec = __fadd_rn(spec, __fdiv_rn(s, static_cast<float>(d)));
-          const int slot = emit_f >= 0 ? slot_of(f) : -1;
-          if (slot >= 0) {
-            a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-            spec = 0.0f;
           }
         }
       }
       __threadfence_block();
-      bar_arrive(kBarFull + (tile & 1), kDetectThreads);  // hand the averaged tile to the box warps
-      bar_sync(kBarMarch, kMarchThreads);                 // every march thread is done with tile-1's PSD buffer
-      issue_tile(tile + 2);                               // ... which tile+2 reuses
+      bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of sums to the box warps
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_empty[ps]);               // the PSD slot may be refilled
+      if (Y_T > 0) {
+#pragma unroll
+        for (int f = 0; f < YC; ++f) lead[f] = q[TF - YC + f];
+        lead_valid = tf == TF;
+      }
     }
-    cp_async_wait<0>();
     if (owner) {
       a.threshold[j] = thr;
       a.avg_sum[j] = sum;
-      a.avg_last[j] = last_avg;
+      a.avg_last[j] = (T > 0 && a.avg_frames + T >= Y) ? __fdiv_rn(sum, static_cast<float>(Y)) : kNoData;
       // ring after the push, oldest -> newest: row i is in-push frame T - Y + i, or a surviving row of ring_in
-      for (int i = 0; i < Y; ++i) {
-        const int t = T - Y + i;
-        float q;
-        if (t >= 0) {
-          q = noise_sub(a.psd[static_cast<size_t>(t) * n + j], thr, a.noise_samples + t < a.learn_frames);
-        } else {
-          q = a.ring_in[static_cast<size_t>(T + i) * n + j];
+      for (int i0 = 0; i0 < Y; i0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u, t = T - Y + i;
+          v[u] = 0.0f;
+          if (i < Y) v[u] = (t >= 0) ? psd[static_cast<size_t>(t) * n + j] : ring_in[static_cast<size_t>(T + i) * n + j];
         }
-        a.ring_out[static_cast<size_t>(i) * n + j] = q;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u, t = T - Y + i;
+          if (i < Y) a.ring_out[static_cast<size_t>(i) * n + j] = (t >= 0) ? noise_sub(v[u], thr, a.noise_samples + t < a.learn_frames) : v[u];
+        }
       }
     }
+  } else if (tid < kSumThreads + kSpecThreads) {
+    // ============================================ SPEC warps ============================================
+    const int k = tid - kSumThreads;   // owned bin j0 + k, column hp + k
+    const int j = j0 + k;
+    const int d = a.spec_out > 0 ? n / a.spec_out : 0;
+    const bool spec_owner = d > 0 && j < n && (j % d) == 0;
+    float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
+    int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int t0 = tile * TF;
+      const int tf = min(TF, T - t0);
+      const int ps = tile % kDetectBuffers;
+      const float* __restrict__ cur = psd_tiles + ps * tile_elems + hp + k;
+      mbar_wait_sleepy(&p_full[ps], (tile / kDetectBuffers) & 1);
+      if (spec_owner) {
+        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
+        const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
+        if (d == 1 && !emits && tf == TF) {  // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49)
+          float p[TF];
+#pragma unroll
+          for (int f = 0; f < TF; ++f) p[f] = cur[f * width];
+#pragma unroll
+          for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, p[f]);
+        } else {
+          for (int f = 0; f < tf; ++f) {
+            float s = cur[f * width];
+            if (d > 1) {  // decimating spectrogram: mean of d adjacent raw bins, then accumulate (spectrogram.cpp:50-58)
+              s = 0.0f;
+              for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + i]);
+              s = __fdiv_rn(s, static_cast<float>(d));
+            }
+            spec = __fadd_rn(spec, s);
+            int slot = -1;  // planned row emitted after frame t0 + f
+            for (int i = next_emit; emits && i < a.n_emit && a.emit_frame[i] <= t0 + f; ++i) slot = (a.emit_frame[i] == t0 + f) ? i : slot;
+            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
+              spec = 0.0f;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_empty[ps]);
+    }
     if (spec_owner) a.spec_sum[j / d] = spec;
+  } else if (tid < kSumThreads + kSpecThreads + 32) {
+    // ============================================ PRODUCER warp ============================================
+    const int c_lo = max(0, -col0), c_hi = min(width, n - col0);  // columns that exist in the row
+#if B2S_K2_BULK_ROWS
+    const uint32_t row_bytes = static_cast<uint32_t>(c_hi - c_lo) * sizeof(float);
+#endif
+    const int chunks_per_row = (c_hi - c_lo) / 4;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int t0 = tile * TF;
+      const int tf = min(TF, T - t0);
+      const int ps = tile % kDetectBuffers;
+      mbar_wait_sleepy(&p_empty[ps], ((tile / kDetectBuffers) & 1) ^ 1);  // both consumer groups released the slot (passes at once for the first round)
+#if B2S_K2_BULK_ROWS
+      if (lane == 0) mbar_arrive_expect_tx(&p_full[ps], row_bytes * tf);
+      __syncwarp();
+      if (lane < tf) bulk_g2s(psd_tiles + ps * tile_elems + lane * width + c_lo, psd + static_cast<size_t>(t0 + lane) * n + col0 + c_lo, row_bytes, &p_full[ps]);
+#else
+      float* dst = psd_tiles + ps * tile_elems + c_lo;
+      const float* src = psd + static_cast<size_t>(t0) * n + col0 + c_lo;
+      for (int f = 0; f < tf; ++f)
+        for (int x = lane; x < chunks_per_row; x += 32) cp_async16(dst + f * width + 4 * x, src + static_cast<size_t>(f) * n + 4 * x);
+      cp_async_mbar_arrive(&p_full[ps]);  // counts as this lane's arrival once all of its copies above have landed
+#endif
+    }
+  } else if (tid < kSumThreads + kSpecThreads + 64) {
+    // ============================================ FLUSH warp ============================================
+    // lane = frame of the tile: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list, then the
+    // staged entries are copied out. Keeps the atomic's round trip off the box warps' path.
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int t0 = tile * TF;
+      const int tf = min(TF, T - t0);
+      const int sb = tile & 1;
+      bar_sync(kBarStageFull + sb, kBoxThreads + 32);
+      int cnt = 0, base = 0;
+      if (lane < tf) {
+        cnt = stage_count[sb * TF + lane];
+        if (cnt > 0) base = atomicAdd(a.slot_count + t0 + lane, cnt);
+      }
+      for (int i = 0; i < cnt; ++i) {  // every lane drains its own frame: short lists, all 32 frames in flight at once
+        if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + lane) * a.slot_capacity + base + i] = stage[(sb * TF + lane) * kDetectBinsPerCta + i];
+      }
+      if (cnt > 0) stage_count[sb * TF + lane] = 0;
+      __threadfence_block();
+      if (tile + 2 < n_tiles) bar_arrive(kBarStageEmpty + sb, kBoxThreads + 32);
+    }
   } else {
     // ============================================ BOX warps ============================================
     // warp w owns the 8-bin segment w of the CTA's 128 bins; lane = frame of the tile
-    const int btid = tid - kMarchThreads;
-    const int lane = btid & 31, seg = btid >> 5;
+    const int btid = tid - (kDetectThreads - kBoxThreads);
+    const int seg = btid >> 5;
     constexpr int SEG = kBoxSegment;
     static_assert(kBoxThreads / 32 == kDetectBinsPerCta / kBoxSegment && kDetectTileFrames == 32, "one box warp per segment, one lane per frame");
     const int b0 = seg * SEG, bin0 = j0 + b0;
     for (int tile = 0; tile < n_tiles; ++tile) {
-      const int t0 = tile * kDetectTileFrames;
-      const int tf = min(kDetectTileFrames, T - t0);
-      bar_sync(kBarFull + (tile & 1), kDetectThreads);  // the march warps have written this average tile
-      const float* avg_tile = avg_tiles + (tile & 1) * avg_elems;
+      const int t0 = tile * TF;
+      const int tf = min(TF, T - t0);
+      const int sb = tile & 1;
+      bar_sync(kBarFull + sb, kSumThreads + kBoxThreads);  // the SUM warps have written this tile
+      const float* avg_tile = sum_tiles + sb * sum_elems;
       const int f = lane, t = t0 + f;
+      float box[SEG];
+      bool have = false;
       if (f < tf && bin0 < n) {
-        float box[SEG];
+        have = true;
         if (HALF_T > 0) {
           constexpr int H = HALF_T > 0 ? HALF_T : 1;
           float w[SEG + 2 * H];
 #pragma unroll
-          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kAvgPitch + f];  // columns outside [0, N) hold 0.0f
-          boxcar_segment<H>(w, box);
+          for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kSumPitch + f];  // columns outside [0, N) hold 0.0f
           if (segment_interior(bin0, n, half)) {
+            boxcar_segment<H>(w, box);
 #pragma unroll
             for (int k = 0; k < SEG; ++k) box[k] = div_const_fast<2 * H + 1>(box[k]);
-          } else {
+          } else {  // a row end cuts some windows: the boxcar sees the zero-extended row and divides by the clipped count
+            boxcar_segment<H>(w, box);
 #pragma unroll
             for (int k = 0; k < SEG; ++k) box[k] = __fdiv_rn(box[k], static_cast<float>(boxcar_count(bin0 + k, n, half)));
           }
@@ -460,9 +510,14 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
 #pragma unroll
           for (int k = 0; k < SEG; ++k) {
             const int bin = bin0 + k;
-            box[k] = (bin >= n) ? -INFINITY : boxcar_value([&](int bb) { return avg_tile[(hp + (bb - j0)) * kAvgPitch + f]; }, bin, n, half);
+            box[k] = (bin >= n) ? -INFINITY
+                                : boxcar_value([&](int bb) { return avg_tile[(hp + (bb - j0)) * kSumPitch + f]; }, bin, n, half);
           }
         }
+      }
+      if (tile + 2 < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten (tile + 2)
+      if (tile >= 2) bar_sync(kBarStageEmpty + sb, kBoxThreads + 32);                  // the flush warp has drained this staging buffer
+      if (have) {
         float top = box[0];
 #pragma unroll
         for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
@@ -500,30 +555,15 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             if (bin < n) {
               if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
               if (box[k] >= a.detect_level) {
-                const int pos = atomicAdd(stage_count + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
-                stage[f * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
+                const int pos = atomicAdd(stage_count + sb * TF + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
+                stage[(sb * TF + f) * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
               }
             }
           }
         }
       }
-      bar_arrive(kBarEmpty + (tile & 1), kDetectThreads);  // this average buffer may be overwritten (tile + 2)
-      bar_sync(kBarBox, kBoxThreads);                      // all entries of the tile are staged
-      // flush: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list
-      if (btid < tf) {
-        const int cnt = stage_count[btid];
-        stage_base[btid] = cnt > 0 ? atomicAdd(a.slot_count + t0 + btid, cnt) : 0;
-      }
-      bar_sync(kBarBox, kBoxThreads);
-      for (int f = btid >> 5; f < tf; f += kBoxThreads >> 5) {  // one warp per frame
-        const int cnt = stage_count[f], base = stage_base[f];
-        for (int i = btid & 31; i < cnt; i += 32) {
-          if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + f) * a.slot_capacity + base + i] = stage[f * kDetectBinsPerCta + i];
-        }
-        __syncwarp();
-        if ((btid & 31) == 0) stage_count[f] = 0;
-      }
-      bar_sync(kBarBox, kBoxThreads);  // staging area re-armed before the next tile's entries arrive
+      __threadfence_block();
+      bar_arrive(kBarStageFull + sb, kBoxThreads + 32);  // hand the staged entries of this tile to the flush warp
     }
   }
 }
