@@ -154,6 +154,8 @@ typedef struct b2s_profile {
   int64_t spectral_launches, detect_launches, window_launches;
   int64_t pushes, frames;
   int64_t h2d_bytes, d2h_bytes; /* bytes moved by b2s_band_push itself */
+  /* load balance of K2 (one CTA per 128 bins): per-CTA run time in ms, median and slowest, summed over launches */
+  double detect_cta_median_ms, detect_cta_max_ms;
 } b2s_profile;
 int b2s_band_set_profiling(b2s_band* b, int enable);
 int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset);

@@ -92,6 +92,8 @@ class Profile(C.Structure):
         ("frames", C.c_int64),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("detect_cta_median_ms", C.c_double),
+        ("detect_cta_max_ms", C.c_double),
     ]
 
 

@@ -41,6 +41,7 @@ struct PushSlot {
   DevBuf<DetectEntry> sorted;
   DevBuf<signed char> spec_rows;
   DevBuf<unsigned int> watch_max;
+  DevBuf<unsigned long long> cta_ns;
   DevBuf<int> cand_flag;
   PinBuf<int> h_offsets, h_cand_flag;
   PinBuf<unsigned int> h_watch_max;
@@ -66,7 +67,7 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
-    h_offsets.release(); h_entries.release(); watch_max.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
+    h_offsets.release(); h_entries.release(); watch_max.release(); cta_ns.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
     if (gpu_done) cudaEventDestroy(gpu_done);
     for (auto& e : ev) {
       if (e) cudaEventDestroy(e);
@@ -545,6 +546,11 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     da.emit_div[i] = emit_divs[i];
   }
   da.spec_rows = s.spec_rows.p;
+  da.cta_ns = nullptr;
+  if (profiling) {
+    if ((rc = s.cta_ns.alloc(2 * ((n + kDetectBinsPerCta - 1) / kDetectBinsPerCta)))) return rc;
+    da.cta_ns = s.cta_ns.p;
+  }
   da.dense_q = s.dense_q_on ? s.dense_q.p : nullptr;
   da.dense_avg = s.dense_avg_on ? s.dense_avg.p : nullptr;
   da.dense_box = s.dense_box_on ? s.dense_box.p : nullptr;
@@ -552,8 +558,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * (kDetectBuffers * kDetectTileFrames * width + 2 * width * (kDetectTileFrames + 1)) +
-                        2 * (sizeof(int) * kDetectTileFrames + sizeof(DetectEntry) * kDetectTileFrames * kDetectBinsPerCta);
+    const size_t smem = sizeof(float) * (kDetectBuffers * kDetectTileFrames * width + 2 * width * (kDetectTileFrames + 1) +
+                                         kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {
@@ -626,6 +632,16 @@ int b2s_band::finish_chunk(PushSlot& s) {
     prof.spectral_ms += ms;
     CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
     prof.detect_ms += ms;
+    if (s.cta_ns.p) {
+      const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+      std::vector<unsigned long long> ns(2 * grid);
+      CU(cudaMemcpy(ns.data(), s.cta_ns.p, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost));
+      std::vector<double> dur(grid);
+      for (int i = 0; i < grid; ++i) dur[i] = static_cast<double>(ns[2 * i + 1] - ns[2 * i]) * 1e-6;
+      std::sort(dur.begin(), dur.end());
+      prof.detect_cta_median_ms += dur[grid / 2];
+      prof.detect_cta_max_ms += dur[grid - 1];
+    }
   }
   const auto host_t0 = std::chrono::steady_clock::now();
   if (*h_max > slot_capacity) return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries; detect_capacity is %d per frame", *h_max, slot_capacity);

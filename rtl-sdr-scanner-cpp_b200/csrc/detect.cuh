@@ -23,7 +23,7 @@ namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
-constexpr int kDetectBuffers = 3;       // PSD tiles resident in the shared ring (being consumed / landed / in flight)
+constexpr int kDetectBuffers = 4;       // PSD tiles resident in the shared ring (being consumed / landed / in flight)
 constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
 constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
@@ -76,6 +76,7 @@ struct DetectArgs {
   int emit_frame[kMaxSpecEmits];   // frame after which row i is emitted (ascending)
   int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
   signed char* spec_rows;          // [n_emit][M]
+  unsigned long long* cta_ns;      // optional [2 * grid]: %globaltimer at CTA start / end (profiling: load balance)
   // optional dense rows [T][N]
   float* dense_q;
   float* dense_avg;
@@ -138,9 +139,9 @@ inline float ordered_to_float(unsigned int u) {
   return f;
 }
 
-constexpr int kBoxSegment = 8;  // bins per boxcar segment (segments are aligned to multiples of 8 bins)
+constexpr int kBoxSegment = 16;  // bins per boxcar segment (segments are aligned to multiples of 16 bins)
 
-// Boxcar running sums of one aligned segment of 8 bins over the ZERO-EXTENDED row: w[i] holds the averaged value of bin
+// Boxcar running sums of one aligned segment of kBoxSegment bins over the ZERO-EXTENDED row: w[i] holds the averaged value of bin
 // (b0 - H + i), i in [0, 8 + 2H), with 0.0f wherever that bin lies outside [0, N) (adding or subtracting 0.0f is exact,
 // so clipped windows come out as the left-to-right sum of their valid bins). sums[0] = w[0] + w[1] + ... + w[2H];
 // sums[k] continues the running sum exactly like utils.cpp:41-48: drop the leaving element, then add the entering one.
@@ -187,6 +188,11 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 #ifndef B2S_K2_BULK_ROWS
 #define B2S_K2_BULK_ROWS 1  // 1: one cp.async.bulk per row (one instruction per lane and tile); 0: LDGSTS chunks (the issue loop alone costs ~10k cycles per tile)
 #endif
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // named barriers (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -195,12 +201,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 // Warp roles of k_detect. One CTA owns kDetectBinsPerCta bins plus a halo of X/2 bins (rounded up to 4) on each side,
 // computed redundantly; every role walks the push in tiles of kDetectTileFrames frames and the roles meet only through
 // mbarriers, so each runs as far ahead as its buffers allow.
-constexpr int kSumWarps = 6, kSpecWarps = 4, kBoxWarps = kDetectBinsPerCta / 8;
+#ifndef B2S_K2_DIV_IN_BOX
+#define B2S_K2_DIV_IN_BOX 0  // 1: steady tiles carry m_sum and the box lanes divide (more total work, shorter serial chain)
+#endif
+#ifndef B2S_K2_BOX_GROUPS
+#define B2S_K2_BOX_GROUPS 2
+#endif
+constexpr int kBoxGroups = B2S_K2_BOX_GROUPS;  // box-warp groups; group g takes the tiles with (tile % kBoxGroups) == g (1 or 2)
+constexpr int kSumWarps = 6, kSpecWarps = 4, kBoxWarps = kDetectBinsPerCta / kBoxSegment;
 constexpr int kSumThreads = 32 * kSumWarps;    // one thread per column (<= 192 columns)
 constexpr int kSpecThreads = 32 * kSpecWarps;  // one thread per owned bin
-constexpr int kBoxThreads = 32 * kBoxWarps;    // one warp per 8-bin segment, lane = frame of the tile
-constexpr int kDetectThreads = kSumThreads + kSpecThreads + 32 /*producer*/ + 32 /*flush*/ + kBoxThreads;
-constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/, kBarStageFull = 6 /*,7*/, kBarStageEmpty = 8 /*,9*/;  // hardware barriers: waiting warps sleep instead of polling
+constexpr int kBoxThreads = 32 * kBoxWarps;    // threads of ONE box group: one warp per boxcar segment, lane = frame of the tile
+constexpr int kDetectThreads = kSumThreads + kSpecThreads + 32 /*producer*/ + kBoxGroups * kBoxThreads;
+constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/;  // hardware barriers: waiting warps sleep instead of polling
 
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
 // or 0 / -1 for the generic runtime-parameter instantiation.
@@ -212,9 +225,10 @@ constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/, kBarStageFull = 6 /*,7*
 //                  else lives on this instruction stream: the last Y noise-subtracted values stay in registers from tile to
 //                  tile, and the running sums go to a transposed shared tile (s_full / s_empty).
 //   SPEC warps     (thread = owned bin) Spectrogram::process: the second serial chain (accumulation of raw rows).
-//   BOX warps      (warp = 8-bin segment, lane = frame) m_average = m_sum / Y for the 8 + 2H columns of the segment, boxcar,
-//                  threshold, watched-window maxima; detection entries are staged in shared memory and flushed with one
-//                  global atomic per (CTA, frame).
+//   BOX warps      (warp = 16-bin segment, lane = frame) boxcar over the averaged tile, threshold, watched-window maxima;
+//                  a lane with bins at or above the level reserves room in the frame's slot list with one global atomic
+//                  and writes its entries once the atomic has returned (after the watch block). Two groups of box
+//                  warps take alternate tiles, one per average buffer.
 // Steady-state tiles (no learning frame, ring look-back inside the push, full tile, no dense debug rows) take a
 // register-resident fully unrolled march; all others a generic one with the same float operations in the same order
 // (bit-identical, tested).
@@ -234,8 +248,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   constexpr int kSumPitch = TF + 1;
   const int sum_elems = width * kSumPitch;
   float* sum_tiles = psd_tiles + kDetectBuffers * tile_elems;
-  int* stage_count = reinterpret_cast<int*>(sum_tiles + 2 * sum_elems);  // [2][TF] detection entries staged per frame of the tile
-  DetectEntry* stage = reinterpret_cast<DetectEntry*>(stage_count + 2 * TF);  // [2][TF][kDetectBinsPerCta]
+  float* box_park = sum_tiles + 2 * sum_elems;  // [kBoxGroups][kBoxWarps][kBoxSegment][TF] per-lane scratch of the box warps
   __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];          // watched keys that touch this CTA's bins
   __shared__ __align__(8) uint64_t p_full[kDetectBuffers], p_empty[kDetectBuffers];
 
@@ -266,7 +279,6 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
     }
     fence_barrier_init();
   }
-  if (tid < 2 * TF) stage_count[tid] = 0;
   if (tid < width && (col0 + tid < 0 || col0 + tid >= n)) {  // columns outside the row: the boxcar sees the zero-extended row
     for (int f = 0; f < kSumPitch; ++f) {
       sum_tiles[tid * kSumPitch + f] = 0.0f;
@@ -276,6 +288,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   __syncthreads();
 
   const int lane = tid & 31;
+  if (a.cta_ns && tid == 0) a.cta_ns[2 * blockIdx.x] = global_timer_ns();
   if (tid < kSumThreads) {
     // ============================================ SUM warps ============================================
     const int j = col0 + tid;  // my column's bin
@@ -309,9 +322,10 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       mbar_wait_sleepy(&p_full[ps], (tile / kDetectBuffers) & 1);        // the PSD tile has landed
       if (tile >= 2) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this sum buffer
       float q[TF];
+      float checkpoint = 0.0f;
       if (steady) {
         if (active) {
-          if (owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = sum;  // m_sum before frame t0
+          checkpoint = sum;  // m_sum before frame t0
 #pragma unroll
           for (int f = 0; f < TF; ++f) q[f] = cur[f * width];
 #pragma unroll
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
             const float old = (f >= YC) ? q[f - YC] : lead[f];
             sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
             sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
-            sum_col[f] = div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
+            sum_col[f] = B2S_K2_DIV_IN_BOX ? sum : div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
           }
         }
       } else if (active) {
@@ -354,9 +368,11 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         }
       }
       __threadfence_block();
-      bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of sums to the box warps
+      bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of averages to the box warps
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[ps]);               // the PSD slot may be refilled
+      // global stores only after the hand-over: the fence above must not wait for a DRAM round trip
+      if (steady && owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = checkpoint;
       if (Y_T > 0) {
 #pragma unroll
         for (int f = 0; f < YC; ++f) lead[f] = q[TF - YC + f];
@@ -452,36 +468,18 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       cp_async_mbar_arrive(&p_full[ps]);  // counts as this lane's arrival once all of its copies above have landed
 #endif
     }
-  } else if (tid < kSumThreads + kSpecThreads + 64) {
-    // ============================================ FLUSH warp ============================================
-    // lane = frame of the tile: ONE global atomic per (CTA, frame) reserves a block of the frame's slot list, then the
-    // staged entries are copied out. Keeps the atomic's round trip off the box warps' path.
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      const int t0 = tile * TF;
-      const int tf = min(TF, T - t0);
-      const int sb = tile & 1;
-      bar_sync(kBarStageFull + sb, kBoxThreads + 32);
-      int cnt = 0, base = 0;
-      if (lane < tf) {
-        cnt = stage_count[sb * TF + lane];
-        if (cnt > 0) base = atomicAdd(a.slot_count + t0 + lane, cnt);
-      }
-      for (int i = 0; i < cnt; ++i) {  // every lane drains its own frame: short lists, all 32 frames in flight at once
-        if (base + i < a.slot_capacity) a.slots[static_cast<size_t>(t0 + lane) * a.slot_capacity + base + i] = stage[(sb * TF + lane) * kDetectBinsPerCta + i];
-      }
-      if (cnt > 0) stage_count[sb * TF + lane] = 0;
-      __threadfence_block();
-      if (tile + 2 < n_tiles) bar_arrive(kBarStageEmpty + sb, kBoxThreads + 32);
-    }
   } else {
     // ============================================ BOX warps ============================================
-    // warp w owns the 8-bin segment w of the CTA's 128 bins; lane = frame of the tile
-    const int btid = tid - (kDetectThreads - kBoxThreads);
+    // warp w owns segment w (kBoxSegment bins) of the CTA's 128 bins; lane = frame of the tile
+    const int group = (tid - (kDetectThreads - kBoxGroups * kBoxThreads)) / kBoxThreads;
+    const int btid = tid - (kDetectThreads - kBoxGroups * kBoxThreads) - group * kBoxThreads;
     const int seg = btid >> 5;
     constexpr int SEG = kBoxSegment;
     static_assert(kBoxThreads / 32 == kDetectBinsPerCta / kBoxSegment && kDetectTileFrames == 32, "one box warp per segment, one lane per frame");
     const int b0 = seg * SEG, bin0 = j0 + b0;
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    float* my_box = box_park + (group * kBoxWarps + seg) * SEG * TF + lane;  // [k * TF]: written and read by this lane only
+    static_assert(kBoxGroups == 1 || kBoxGroups == 2, "the average tile is double-buffered: at most one group per buffer");
+    for (int tile = group; tile < n_tiles; tile += kBoxGroups) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
       const int sb = tile & 1;
@@ -497,6 +495,10 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
           float w[SEG + 2 * H];
 #pragma unroll
           for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kSumPitch + f];  // columns outside [0, N) hold 0.0f
+          if (B2S_K2_DIV_IN_BOX && Y_T > 0 && tf == TF && t0 >= Y && (a.noise_samples + t0 >= a.learn_frames) && !dense) {  // a steady tile holds sums
+#pragma unroll
+            for (int i = 0; i < SEG + 2 * H; ++i) w[i] = div_const_fast<(Y_T > 0 ? Y_T : 1)>(w[i]);
+          }
           if (segment_interior(bin0, n, half)) {
             boxcar_segment<H>(w, box);
 #pragma unroll
@@ -516,55 +518,68 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         }
       }
       if (tile + 2 < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten (tile + 2)
-      if (tile >= 2) bar_sync(kBarStageEmpty + sb, kBoxThreads + 32);                  // the flush warp has drained this staging buffer
+      // bins at or above the detection level: reserve room in the frame's slot list now (one atomic per lane with hits);
+      // the entries are written after the watch block below, when the atomic's round trip has been paid by other work
+      unsigned int hits = 0;  // bit k: bin0 + k is at or above the detection level in my frame
+      float top = -INFINITY;
+      bool parked = false;
+      int pos = 0;
       if (have) {
-        float top = box[0];
+        top = box[0];
 #pragma unroll
         for (int k = 1; k < SEG; ++k) top = fmaxf(top, box[k]);
-        // watched keys: window maxima over ALL bins (also below the detection level), and the uncovered-candidate flag
-        if (rel_n > 0 || top >= a.start_level) {
-          const int gh = a.group_size / 2, margin = (a.group_size % 2 == 0) ? gh : gh + 1;
-          unsigned int covered = 0;  // bit k: bin0 + k lies inside some key's containsWithMargin interval
-          for (int r = 0; r < rel_n; ++r) {
-            const int key = rel_key[r], w = rel_slot[r];
-            if (bin0 + SEG - 1 >= key - gh && bin0 <= key + gh) {
-              float m = -INFINITY;
+        if (a.dense_box) {
 #pragma unroll
-              for (int k = 0; k < SEG; ++k) {
-                const int bin = bin0 + k;
-                if (bin < n && bin >= key - gh && bin <= key + gh) m = fmaxf(m, box[k]);
-              }
-              if (m > -INFINITY) atomicMax(a.watch_max + static_cast<size_t>(t) * kMaxWatch + w, float_to_ordered(m));
-            }
-            if (bin0 + SEG - 1 >= key - margin && bin0 <= key + margin) {
-#pragma unroll
-              for (int k = 0; k < SEG; ++k) covered |= (bin0 + k >= key - margin && bin0 + k <= key + margin) ? (1u << k) : 0u;
-            }
-          }
-          if (top >= a.start_level) {
-            bool uncovered = false;
-#pragma unroll
-            for (int k = 0; k < SEG; ++k) uncovered |= (bin0 + k < n) && box[k] >= a.start_level && !((covered >> k) & 1u);
-            if (uncovered) a.cand_flag[t] = 1;
-          }
+          for (int k = 0; k < SEG; ++k)
+            if (bin0 + k < n) a.dense_box[static_cast<size_t>(t) * n + bin0 + k] = box[k];
         }
-        if (a.dense_box || top >= a.detect_level) {
+        if (top >= a.detect_level) {
 #pragma unroll
-          for (int k = 0; k < SEG; ++k) {
-            const int bin = bin0 + k;
-            if (bin < n) {
-              if (a.dense_box) a.dense_box[static_cast<size_t>(t) * n + bin] = box[k];
-              if (box[k] >= a.detect_level) {
-                const int pos = atomicAdd(stage_count + sb * TF + f, 1);  // shared-memory counter: at most 128 entries per frame per CTA
-                stage[(sb * TF + f) * kDetectBinsPerCta + pos] = DetectEntry{bin, box[k]};
-              }
-            }
-          }
+          for (int k = 0; k < SEG; ++k) hits |= (bin0 + k < n && box[k] >= a.detect_level) ? (1u << k) : 0u;
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) my_box[k * TF] = box[k];  // parked: the write-out below indexes them dynamically
+          parked = true;
+          pos = atomicAdd(a.slot_count + t, __popc(hits));
         }
       }
-      __threadfence_block();
-      bar_arrive(kBarStageFull + sb, kBoxThreads + 32);  // hand the staged entries of this tile to the flush warp
+      // watched keys: window maxima over ALL bins (also below the detection level), and the uncovered-candidate flag
+      if (have && (rel_n > 0 || top >= a.start_level)) {
+        const int gh = a.group_size / 2, margin = (a.group_size % 2 == 0) ? gh : gh + 1;
+        const int last = min(bin0 + SEG, n) - 1 - bin0;  // last valid bin of the segment (local)
+        unsigned int covered = 0;  // bit k: bin0 + k lies inside some key's containsWithMargin interval
+        for (int r = 0; r < rel_n; ++r) {
+          const int key = rel_key[r] - bin0, w = rel_slot[r];  // key position relative to the segment
+          const int lo = max(key - gh, 0), hi = min(key + gh, last);
+          if (lo <= hi) {  // the key's window touches this segment (same for every lane of the warp)
+            if (!parked) {  // park my values in shared memory once: the windows below index them dynamically
+#pragma unroll
+              for (int k = 0; k < SEG; ++k) my_box[k * TF] = box[k];
+              parked = true;
+            }
+            float m = my_box[lo * TF];
+            for (int k = lo + 1; k <= hi; ++k) m = fmaxf(m, my_box[k * TF]);
+            atomicMax(a.watch_max + static_cast<size_t>(t) * kMaxWatch + w, float_to_ordered(m));
+          }
+          const int clo = max(key - margin, 0), chi = min(key + margin, SEG - 1);
+          if (clo <= chi) covered |= ((2u << (chi - clo)) - 1u) << clo;
+        }
+        if (top >= a.start_level) {
+          unsigned int over = 0;
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) over |= (k <= last && box[k] >= a.start_level) ? (1u << k) : 0u;
+          if (over & ~covered) a.cand_flag[t] = 1;
+        }
+      }
+      if (hits) {  // detection entries of my (frame, segment), bins ascending; the per-frame list is ordered later (k_entries_sort)
+        DetectEntry* dst = a.slots + static_cast<size_t>(t) * a.slot_capacity;
+        for (unsigned int mm = hits; mm; mm &= mm - 1) {
+          const int k = __ffs(mm) - 1;
+          if (pos < a.slot_capacity) dst[pos] = DetectEntry{bin0 + k, my_box[k * TF]};
+          ++pos;
+        }
+      }
     }
+    if (a.cta_ns && btid == 0 && group == (n_tiles - 1) % kBoxGroups) a.cta_ns[2 * blockIdx.x + 1] = global_timer_ns();
   }
 }
 
