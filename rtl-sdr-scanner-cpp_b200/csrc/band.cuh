@@ -558,8 +558,12 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
-    const size_t smem = sizeof(float) * (kDetectBuffers * kDetectTileFrames * width + 2 * width * (kDetectTileFrames + 1) +
-                                         kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
+    constexpr size_t kSmemBudget = 220 * 1024;
+    const size_t fixed = sizeof(float) * (2 * width * (kDetectTileFrames + 1) + kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
+    const size_t per_tile = sizeof(float) * kDetectTileFrames * width;
+    da.n_buffers = static_cast<int>(std::min<size_t>(kDetectBuffers, (kSmemBudget - fixed) / per_tile));
+    if (const char* e = getenv("B2S_K2_BUFFERS")) da.n_buffers = std::max(2, std::min(da.n_buffers, atoi(e)));  // experiments
+    const size_t smem = fixed + per_tile * da.n_buffers;
     const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
     static bool configured = false;
     if (!configured) {

@@ -23,7 +23,7 @@ namespace b2s {
 
 constexpr int kDetectBinsPerCta = 128;  // bins owned by one CTA (also the largest spectrogram decimation supported)
 constexpr int kDetectTileFrames = 32;   // frames per shared-memory tile
-constexpr int kDetectBuffers = 4;       // PSD tiles resident in the shared ring (being consumed / landed / in flight)
+constexpr int kDetectBuffers = 6;       // at most this many PSD tiles in the shared ring (DetectArgs::n_buffers: what fits)
 constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk) may complete
 constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
@@ -39,6 +39,7 @@ struct DetectArgs {
   int n_frames;  // T
   int group_y;   // Averager depth Y
   int group_x;   // boxcar width X
+  int n_buffers; // PSD tiles in the shared-memory ring (2..kDetectBuffers)
   // inputs
   const float* psd;  // [T][N] raw PSD rows from K1
   // noise state (per centre frequency)
@@ -178,16 +179,6 @@ __device__ __forceinline__ float boxcar_value(At at, int j, int n, int half) {
   return __fdiv_rn(s, static_cast<float>(boxcar_count(j, n, half)));
 }
 
-// 16-byte asynchronous global->shared copy (LDGSTS) and its completion hook on an mbarrier
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-#ifndef B2S_K2_BULK_ROWS
-#define B2S_K2_BULK_ROWS 1  // 1: one cp.async.bulk per row (one instruction per lane and tile); 0: LDGSTS chunks (the issue loop alone costs ~10k cycles per tile)
-#endif
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -208,11 +199,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 #define B2S_K2_BOX_GROUPS 2
 #endif
 constexpr int kBoxGroups = B2S_K2_BOX_GROUPS;  // box-warp groups; group g takes the tiles with (tile % kBoxGroups) == g (1 or 2)
-constexpr int kSumWarps = 6, kSpecWarps = 4, kBoxWarps = kDetectBinsPerCta / kBoxSegment;
+constexpr int kSumWarps = 6, kBoxWarps = kDetectBinsPerCta / kBoxSegment;
 constexpr int kSumThreads = 32 * kSumWarps;    // one thread per column (<= 192 columns)
-constexpr int kSpecThreads = 32 * kSpecWarps;  // one thread per owned bin
 constexpr int kBoxThreads = 32 * kBoxWarps;    // threads of ONE box group: one warp per boxcar segment, lane = frame of the tile
-constexpr int kDetectThreads = kSumThreads + kSpecThreads + 32 /*producer*/ + kBoxGroups * kBoxThreads;
+constexpr int kDetectThreads = kSumThreads + 32 /*producer*/ + kBoxGroups * kBoxThreads;
+// registers per thread: the hardware allocates per warp in units of 512, so 23 warps get at most 2560 = 32 x 80
+constexpr int kDetectRegs = 80;
+static_assert((kDetectThreads / 32) * ((kDetectRegs * 32 + 511) / 512 * 512) <= 65536, "k_detect must fit the register file");
 constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/;  // hardware barriers: waiting warps sleep instead of polling
 
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
@@ -233,7 +226,7 @@ constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/;  // hardware barriers: 
 // register-resident fully unrolled march; all others a generic one with the same float operations in the same order
 // (bit-identical, tested).
 template <int Y_T, int HALF_T>
-__global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
+__global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
   extern __shared__ __align__(128) float sm[];
   constexpr int TF = kDetectTileFrames;
   static_assert(Y_T <= TF, "the register-resident ring look-back needs Y <= tile frames");
@@ -247,7 +240,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
   // frames at once (lane = frame: consecutive words, conflict-free).
   constexpr int kSumPitch = TF + 1;
   const int sum_elems = width * kSumPitch;
-  float* sum_tiles = psd_tiles + kDetectBuffers * tile_elems;
+  float* sum_tiles = psd_tiles + a.n_buffers * tile_elems;
   float* box_park = sum_tiles + 2 * sum_elems;  // [kBoxGroups][kBoxWarps][kBoxSegment][TF] per-lane scratch of the box warps
   __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];          // watched keys that touch this CTA's bins
   __shared__ __align__(8) uint64_t p_full[kDetectBuffers], p_empty[kDetectBuffers];
@@ -273,9 +266,9 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       }
     }
     rel_n = cnt;
-    for (int i = 0; i < kDetectBuffers; ++i) {
-      mbar_init(&p_full[i], B2S_K2_BULK_ROWS ? 1 : 32);
-      mbar_init(&p_empty[i], kSumWarps + kSpecWarps);
+    for (int i = 0; i < a.n_buffers; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], kSumWarps);
     }
     fence_barrier_init();
   }
@@ -301,11 +294,16 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
 #pragma unroll
     for (int f = 0; f < YC; ++f) lead[f] = 0.0f;
     bool lead_valid = false;
+    // Spectrogram::process on the RAW rows (spectrogram.cpp:46-58): a second serial chain, carried by the owner threads
+    const int d = a.spec_out > 0 ? n / a.spec_out : 0;
+    const bool spec_owner = owner && d > 0 && (j % d) == 0;
+    float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
+    int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
 
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
-      const int ps = tile % kDetectBuffers, sb = tile & 1;
+      const int ps = tile % a.n_buffers, sb = tile & 1;
       const float* __restrict__ cur = psd_tiles + ps * tile_elems + tid;
       float* __restrict__ sum_col = sum_tiles + sb * sum_elems + tid * kSumPitch;  // my column of the transposed tile
       const bool steady = Y_T > 0 && tf == TF && t0 >= Y && lead_valid && (a.noise_samples + t0 >= a.learn_frames) && !dense;
@@ -319,24 +317,44 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
           if (f < tf && (f < Y || t < Y)) oldraw[f] = (t < Y) ? ring_in[static_cast<size_t>(t) * n + j] : psd[static_cast<size_t>(t - Y) * n + j];
         }
       }
-      mbar_wait_sleepy(&p_full[ps], (tile / kDetectBuffers) & 1);        // the PSD tile has landed
+      mbar_wait_sleepy(&p_full[ps], (tile / a.n_buffers) & 1);        // the PSD tile has landed
       if (tile >= 2) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this sum buffer
       float q[TF];
       float checkpoint = 0.0f;
+      while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
+      const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;  // a spectrogram row completes inside this tile
+      const bool spec_inline = steady && d == 1 && !emits;
       if (steady) {
         if (active) {
           checkpoint = sum;  // m_sum before frame t0
+          // two halves: the second half of the tile is loaded only when most of `lead` is dead, which keeps the live set at
+          // ~40 frame values instead of 53 (no spills on the serial chain)
+          constexpr int kSplit = TF / 2, kLate = kSplit - 4;
+          const bool spec_here = spec_inline && spec_owner;
+          auto load_half = [&](int f0) {
 #pragma unroll
-          for (int f = 0; f < TF; ++f) q[f] = cur[f * width];
+            for (int f = f0; f < f0 + kSplit; ++f) q[f] = cur[f * width];
+            if (spec_here) {
 #pragma unroll
-          for (int f = 0; f < TF; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
+              for (int f = f0; f < f0 + kSplit; ++f) spec = __fadd_rn(spec, q[f]);
+            }
 #pragma unroll
-          for (int f = 0; f < TF; ++f) {
-            const float old = (f >= YC) ? q[f - YC] : lead[f];
-            sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
-            sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
-            sum_col[f] = B2S_K2_DIV_IN_BOX ? sum : div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
-          }
+            for (int f = f0; f < f0 + kSplit; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
+          };
+          auto march = [&](int f0, int f1) {
+#pragma unroll
+            for (int f = f0; f < f1; ++f) {
+              const float old = (f >= YC) ? q[f - YC] : lead[f];
+              sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
+              sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
+              sum_col[f] = B2S_K2_DIV_IN_BOX ? sum : div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
+            }
+          };
+          load_half(0);
+          march(0, kLate);
+          asm volatile("" ::: "memory");  // keep the compiler from hoisting the second half's loads to the top
+          load_half(kSplit);
+          march(kLate, TF);
         }
       } else if (active) {
         // ---- generic march (learning frames, first tile of a push, partial tiles, dense debug rows, runtime Y) ----
@@ -369,6 +387,24 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
       }
       __threadfence_block();
       bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of averages to the box warps
+      if (spec_owner && !spec_inline) {  // tiles with an emission, decimating spectrograms, non-steady tiles
+        const float* __restrict__ raw = cur;
+        for (int f = 0; f < tf; ++f) {
+          float v = raw[f * width];
+          if (d > 1) {  // mean of d adjacent raw bins, then accumulate (spectrogram.cpp:50-58)
+            v = 0.0f;
+            for (int i = 0; i < d; ++i) v = __fadd_rn(v, raw[f * width + i]);
+            v = __fdiv_rn(v, static_cast<float>(d));
+          }
+          spec = __fadd_rn(spec, v);
+          int slot = -1;  // planned row emitted after frame t0 + f
+          for (int i = next_emit; emits && i < a.n_emit && a.emit_frame[i] <= t0 + f; ++i) slot = (a.emit_frame[i] == t0 + f) ? i : slot;
+          if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
+            a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
+            spec = 0.0f;
+          }
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[ps]);               // the PSD slot may be refilled
       // global stores only after the hand-over: the fence above must not wait for a DRAM round trip
@@ -379,6 +415,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         lead_valid = tf == TF;
       }
     }
+    if (spec_owner) a.spec_sum[j / d] = spec;
     if (owner) {
       a.threshold[j] = thr;
       a.avg_sum[j] = sum;
@@ -399,74 +436,18 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(const DetectArgs a) {
         }
       }
     }
-  } else if (tid < kSumThreads + kSpecThreads) {
-    // ============================================ SPEC warps ============================================
-    const int k = tid - kSumThreads;   // owned bin j0 + k, column hp + k
-    const int j = j0 + k;
-    const int d = a.spec_out > 0 ? n / a.spec_out : 0;
-    const bool spec_owner = d > 0 && j < n && (j % d) == 0;
-    float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
-    int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      const int t0 = tile * TF;
-      const int tf = min(TF, T - t0);
-      const int ps = tile % kDetectBuffers;
-      const float* __restrict__ cur = psd_tiles + ps * tile_elems + hp + k;
-      mbar_wait_sleepy(&p_full[ps], (tile / kDetectBuffers) & 1);
-      if (spec_owner) {
-        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-        const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
-        if (d == 1 && !emits && tf == TF) {  // Spectrogram::process on the RAW rows (spectrogram.cpp:46-49)
-          float p[TF];
-#pragma unroll
-          for (int f = 0; f < TF; ++f) p[f] = cur[f * width];
-#pragma unroll
-          for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, p[f]);
-        } else {
-          for (int f = 0; f < tf; ++f) {
-            float s = cur[f * width];
-            if (d > 1) {  // decimating spectrogram: mean of d adjacent raw bins, then accumulate (spectrogram.cpp:50-58)
-              s = 0.0f;
-              for (int i = 0; i < d; ++i) s = __fadd_rn(s, cur[f * width + i]);
-              s = __fdiv_rn(s, static_cast<float>(d));
-            }
-            spec = __fadd_rn(spec, s);
-            int slot = -1;  // planned row emitted after frame t0 + f
-            for (int i = next_emit; emits && i < a.n_emit && a.emit_frame[i] <= t0 + f; ++i) slot = (a.emit_frame[i] == t0 + f) ? i : slot;
-            if (slot >= 0) {  // Spectrogram::send, spectrogram.cpp:66-72: float -> int8 truncation, then clear
-              a.spec_rows[static_cast<size_t>(slot) * a.spec_out + j / d] = static_cast<signed char>(static_cast<int>(__fdiv_rn(spec, static_cast<float>(a.emit_div[slot]))));
-              spec = 0.0f;
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_empty[ps]);
-    }
-    if (spec_owner) a.spec_sum[j / d] = spec;
-  } else if (tid < kSumThreads + kSpecThreads + 32) {
+  } else if (tid < kSumThreads + 32) {
     // ============================================ PRODUCER warp ============================================
     const int c_lo = max(0, -col0), c_hi = min(width, n - col0);  // columns that exist in the row
-#if B2S_K2_BULK_ROWS
     const uint32_t row_bytes = static_cast<uint32_t>(c_hi - c_lo) * sizeof(float);
-#endif
-    const int chunks_per_row = (c_hi - c_lo) / 4;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
-      const int ps = tile % kDetectBuffers;
-      mbar_wait_sleepy(&p_empty[ps], ((tile / kDetectBuffers) & 1) ^ 1);  // both consumer groups released the slot (passes at once for the first round)
-#if B2S_K2_BULK_ROWS
+      const int ps = tile % a.n_buffers;
+      mbar_wait_sleepy(&p_empty[ps], ((tile / a.n_buffers) & 1) ^ 1);  // both consumer groups released the slot (passes at once for the first round)
       if (lane == 0) mbar_arrive_expect_tx(&p_full[ps], row_bytes * tf);
       __syncwarp();
       if (lane < tf) bulk_g2s(psd_tiles + ps * tile_elems + lane * width + c_lo, psd + static_cast<size_t>(t0 + lane) * n + col0 + c_lo, row_bytes, &p_full[ps]);
-#else
-      float* dst = psd_tiles + ps * tile_elems + c_lo;
-      const float* src = psd + static_cast<size_t>(t0) * n + col0 + c_lo;
-      for (int f = 0; f < tf; ++f)
-        for (int x = lane; x < chunks_per_row; x += 32) cp_async16(dst + f * width + 4 * x, src + static_cast<size_t>(f) * n + 4 * x);
-      cp_async_mbar_arrive(&p_full[ps]);  // counts as this lane's arrival once all of its copies above have landed
-#endif
     }
   } else {
     // ============================================ BOX warps ============================================
