@@ -559,7 +559,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     const int hp = (half + 3) & ~3;
     const int width = kDetectBinsPerCta + 2 * hp;
     constexpr size_t kSmemBudget = 220 * 1024;
-    const size_t fixed = sizeof(float) * (2 * width * (kDetectTileFrames + 1) + kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
+    const size_t fixed = sizeof(float) * (kAvgBuffers * width * (kDetectTileFrames + 1) + kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
     const size_t per_tile = sizeof(float) * kDetectTileFrames * width;
     da.n_buffers = static_cast<int>(std::min<size_t>(kDetectBuffers, (kSmemBudget - fixed) / per_tile));
     if (const char* e = getenv("B2S_K2_BUFFERS")) da.n_buffers = std::max(2, std::min(da.n_buffers, atoi(e)));  // experiments

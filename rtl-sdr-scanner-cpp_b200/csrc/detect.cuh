@@ -206,7 +206,12 @@ constexpr int kDetectThreads = kSumThreads + 32 /*producer*/ + kBoxGroups * kBox
 // registers per thread: the hardware allocates per warp in units of 512, so 23 warps get at most 2560 = 32 x 80
 constexpr int kDetectRegs = 80;
 static_assert((kDetectThreads / 32) * ((kDetectRegs * 32 + 511) / 512 * 512) <= 65536, "k_detect must fit the register file");
-constexpr int kBarFull = 2 /*,3*/, kBarEmpty = 4 /*,5*/;  // hardware barriers: waiting warps sleep instead of polling
+#ifndef B2S_K2_AVG_BUFFERS
+#define B2S_K2_AVG_BUFFERS 2
+#endif
+constexpr int kAvgBuffers = B2S_K2_AVG_BUFFERS;  // average tiles between the SUM and the box warps (a multiple of kBoxGroups)
+static_assert(kAvgBuffers % kBoxGroups == 0 && kAvgBuffers <= 4, "each box group owns whole buffers; barrier ids 2..9");
+constexpr int kBarFull = 2, kBarEmpty = 2 + kAvgBuffers;  // hardware barriers (one pair per average buffer): waiting warps sleep instead of polling
 
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
 // or 0 / -1 for the generic runtime-parameter instantiation.
@@ -241,7 +246,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
   constexpr int kSumPitch = TF + 1;
   const int sum_elems = width * kSumPitch;
   float* sum_tiles = psd_tiles + a.n_buffers * tile_elems;
-  float* box_park = sum_tiles + 2 * sum_elems;  // [kBoxGroups][kBoxWarps][kBoxSegment][TF] per-lane scratch of the box warps
+  float* box_park = sum_tiles + kAvgBuffers * sum_elems;  // [kBoxGroups][kBoxWarps][kBoxSegment][TF] per-lane scratch of the box warps
   __shared__ int rel_n, rel_key[kMaxWatch], rel_slot[kMaxWatch];          // watched keys that touch this CTA's bins
   __shared__ __align__(8) uint64_t p_full[kDetectBuffers], p_empty[kDetectBuffers];
 
@@ -274,8 +279,8 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
   }
   if (tid < width && (col0 + tid < 0 || col0 + tid >= n)) {  // columns outside the row: the boxcar sees the zero-extended row
     for (int f = 0; f < kSumPitch; ++f) {
-      sum_tiles[tid * kSumPitch + f] = 0.0f;
-      sum_tiles[sum_elems + tid * kSumPitch + f] = 0.0f;
+#pragma unroll
+      for (int b = 0; b < kAvgBuffers; ++b) sum_tiles[b * sum_elems + tid * kSumPitch + f] = 0.0f;
     }
   }
   __syncthreads();
@@ -293,36 +298,33 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
     float lead[YC];  // noise-subtracted values of the last Y frames of the previous tile (the rows about to leave the ring)
 #pragma unroll
     for (int f = 0; f < YC; ++f) lead[f] = 0.0f;
-    bool lead_valid = false;
+    // steady tiles: ring look-back inside the push (t0 >= Y), no learning frame left, no dense debug rows
+    int first_steady = 0x7fffffff;
+    if (Y_T > 0 && !dense) first_steady = max((Y + TF - 1) / TF, (max(a.learn_frames - a.noise_samples, 0) + TF - 1) / TF);
     // Spectrogram::process on the RAW rows (spectrogram.cpp:46-58): a second serial chain, carried by the owner threads
     const int d = a.spec_out > 0 ? n / a.spec_out : 0;
     const bool spec_owner = owner && d > 0 && (j % d) == 0;
     float spec = spec_owner ? a.spec_sum[j / d] : 0.0f;
     int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
 
+    int ps = 0;            // PSD ring slot of the current tile and the parity of its mbarrier phase
+    uint32_t ps_phase = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
-      const int ps = tile % a.n_buffers, sb = tile & 1;
+      const int sb = tile % kAvgBuffers;
       const float* __restrict__ cur = psd_tiles + ps * tile_elems + tid;
       float* __restrict__ sum_col = sum_tiles + sb * sum_elems + tid * kSumPitch;  // my column of the transposed tile
-      const bool steady = Y_T > 0 && tf == TF && t0 >= Y && lead_valid && (a.noise_samples + t0 >= a.learn_frames) && !dense;
-      // frames leaving the ring that neither this tile nor `lead` holds: fetched before anything waits (one latency)
-      float oldraw[TF];
-      if (!steady && active) {
-#pragma unroll
-        for (int f = 0; f < TF; ++f) {
-          const int t = t0 + f;
-          oldraw[f] = 0.0f;
-          if (f < tf && (f < Y || t < Y)) oldraw[f] = (t < Y) ? ring_in[static_cast<size_t>(t) * n + j] : psd[static_cast<size_t>(t - Y) * n + j];
-        }
-      }
-      mbar_wait_sleepy(&p_full[ps], (tile / a.n_buffers) & 1);        // the PSD tile has landed
-      if (tile >= 2) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this sum buffer
+      const bool steady = tile >= first_steady && tf == TF;  // the previous tile was full, so `lead` is valid
+      mbar_wait_sleepy(&p_full[ps], ps_phase);                              // the PSD tile has landed
+      if (tile >= kAvgBuffers) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this average buffer
       float q[TF];
       float checkpoint = 0.0f;
-      while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-      const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;  // a spectrogram row completes inside this tile
+      bool emits = false;  // a spectrogram row completes inside this tile
+      if (next_emit < a.n_emit) {
+        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
+        emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
+      }
       const bool spec_inline = steady && d == 1 && !emits;
       if (steady) {
         if (active) {
@@ -358,6 +360,14 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
         }
       } else if (active) {
         // ---- generic march (learning frames, first tile of a push, partial tiles, dense debug rows, runtime Y) ----
+        // frames leaving the ring that this tile does not hold: fetched together (one latency)
+        float oldraw[TF];
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+          const int t = t0 + f;
+          oldraw[f] = 0.0f;
+          if (f < tf && (f < Y || t < Y)) oldraw[f] = (t < Y) ? ring_in[static_cast<size_t>(t) * n + j] : psd[static_cast<size_t>(t - Y) * n + j];
+        }
 #pragma unroll
         for (int f = 0; f < TF; ++f) {
           q[f] = 0.0f;
@@ -407,12 +417,15 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[ps]);               // the PSD slot may be refilled
+      if (++ps == a.n_buffers) {
+        ps = 0;
+        ps_phase ^= 1;
+      }
       // global stores only after the hand-over: the fence above must not wait for a DRAM round trip
       if (steady && owner && (t0 % kCheckpointEvery) == 0) a.checkpoints[static_cast<size_t>(t0 / kCheckpointEvery) * n + j] = checkpoint;
       if (Y_T > 0) {
 #pragma unroll
         for (int f = 0; f < YC; ++f) lead[f] = q[TF - YC + f];
-        lead_valid = tf == TF;
       }
     }
     if (spec_owner) a.spec_sum[j / d] = spec;
@@ -440,14 +453,19 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
     // ============================================ PRODUCER warp ============================================
     const int c_lo = max(0, -col0), c_hi = min(width, n - col0);  // columns that exist in the row
     const uint32_t row_bytes = static_cast<uint32_t>(c_hi - c_lo) * sizeof(float);
+    int ps = 0;
+    uint32_t ps_phase = 1;  // waiting for the "previous" phase passes at once during the first round
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
-      const int ps = tile % a.n_buffers;
-      mbar_wait_sleepy(&p_empty[ps], ((tile / a.n_buffers) & 1) ^ 1);  // both consumer groups released the slot (passes at once for the first round)
+      mbar_wait_sleepy(&p_empty[ps], ps_phase);  // both consumer groups released the slot (passes at once for the first round)
       if (lane == 0) mbar_arrive_expect_tx(&p_full[ps], row_bytes * tf);
       __syncwarp();
       if (lane < tf) bulk_g2s(psd_tiles + ps * tile_elems + lane * width + c_lo, psd + static_cast<size_t>(t0 + lane) * n + col0 + c_lo, row_bytes, &p_full[ps]);
+      if (++ps == a.n_buffers) {
+        ps = 0;
+        ps_phase ^= 1;
+      }
     }
   } else {
     // ============================================ BOX warps ============================================
@@ -459,11 +477,11 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
     static_assert(kBoxThreads / 32 == kDetectBinsPerCta / kBoxSegment && kDetectTileFrames == 32, "one box warp per segment, one lane per frame");
     const int b0 = seg * SEG, bin0 = j0 + b0;
     float* my_box = box_park + (group * kBoxWarps + seg) * SEG * TF + lane;  // [k * TF]: written and read by this lane only
-    static_assert(kBoxGroups == 1 || kBoxGroups == 2, "the average tile is double-buffered: at most one group per buffer");
+    static_assert(kBoxGroups == 1 || kBoxGroups == 2, "group g takes the tiles with tile % kBoxGroups == g");
     for (int tile = group; tile < n_tiles; tile += kBoxGroups) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
-      const int sb = tile & 1;
+      const int sb = tile % kAvgBuffers;
       bar_sync(kBarFull + sb, kSumThreads + kBoxThreads);  // the SUM warps have written this tile
       const float* avg_tile = sum_tiles + sb * sum_elems;
       const int f = lane, t = t0 + f;
@@ -498,7 +516,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a) {
           }
         }
       }
-      if (tile + 2 < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten (tile + 2)
+      if (tile + kAvgBuffers < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten
       // bins at or above the detection level: reserve room in the frame's slot list now (one atomic per lane with hits);
       // the entries are written after the watch block below, when the atomic's round trip has been paid by other work
       unsigned int hits = 0;  // bit k: bin0 + k is at or above the detection level in my frame
