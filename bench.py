@@ -11,7 +11,7 @@ reference's mailbox does; the timed region ends with b2s_band_sync, i.e. after A
   value : steady-state throughput with the IQ already resident in HBM (B2S_FLAG_IQ_ON_DEVICE), CUDA-event timed.
   e2e   : the same call with the IQ in pinned HOST memory: the host->device copy of every step's input and the
           device->host read of its results are inside the timed region.
-  roofline : dominant kernel (K1 k_spectrum): algorithmic bytes 6 B/sample (2 B int8 IQ read + 4 B fp32 dB row written,
+  roofline : dominant kernel (K1 k_spectrum3): algorithmic bytes 6 B/sample (2 B int8 IQ read + 4 B fp32 dB row written,
           SURVEY.md §8d) x T x N per launch / that kernel's mean launch time (CUDA events inside the library, on the
           launching stream) vs. the measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline : the CPU oracle port (fp32, oracle/liboracle.so — FFTW itself is not available here) on a bounded
@@ -42,11 +42,12 @@ SAMPLE_RATE = 20_000_000
 FRAMES = 4096
 LEARN = 100
 ALG_BYTES_PER_SAMPLE = 6.0
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_spectrum<16384> launch of this workload, from the committed
-# `ncu --set full` capture profiles/r01_k1_v1.1_ncu_summary.txt (134.5 MB read + 209.3 MB written; part of the 268 MB of
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_spectrum3<16> launch of this workload, from the committed
+# `ncu --set full` capture profiles/r01_k1_v3_ncu_summary.txt (134.5 MB read + 210.2 MB written; part of the 268 MB of
 # rows is still dirty in the 126 MB L2 when the kernel ends)
-K1_DRAM_TRAFFIC_BYTES = 343.8e6
-K1_TRAFFIC_SOURCE = "profiles/r01_k1_v1.1_ncu_summary.txt"
+K1_DRAM_TRAFFIC_BYTES = 344.7e6
+K1_TRAFFIC_SOURCE = "profiles/r01_k1_v3_ncu_summary.txt"
+K2_ALG_BYTES_PER_SAMPLE = 4.0  # k_detect reads every fp32 dB row once (its outputs are sparse)
 METRIC = "IQ MSamples/s through FFT+power+detect"
 
 
@@ -270,7 +271,9 @@ def main():
     k1_ms = prof.spectral_ms / max(prof.spectral_launches, 1)
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_SAMPLE * samples_step / (k1_ms / 1000.0) / 1e9
-    launches = int(prof.spectral_launches + prof.detect_launches + prof.window_launches)
+    # kernels of this library per step: k_spectrum3, k_detect, k_entries_prefix, k_entries_sort (+ k_window_query when the tracker asks)
+    launches = int(prof.spectral_launches + 3 * prof.detect_launches + prof.window_launches)
+    k2_ms = prof.detect_ms / max(prof.detect_launches, 1)
     band.close()
 
     # ---- end-to-end run: pinned host IQ, H2D inside the timed region ----
@@ -317,10 +320,14 @@ def main():
             "config": {"workload": "configs[1]: single 20 MS/s band, 16384-pt FFT, fused unpack+FFT+power+detect", "fft_size": N_FFT, "sample_rate_hz": SAMPLE_RATE,
                        "frames_per_step": T, "bands_per_gpu": 1, "input": "int8 IQ (CS8)", "l2": "134 MB input per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"bands sharded, {world} GPU(s), no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "k_spectrum<16384>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": K1_DRAM_TRAFFIC_BYTES if T == FRAMES else None, "traffic_source": K1_TRAFFIC_SOURCE,
+            "roofline": {"bound": "hbm", "kernel": "k_spectrum3<16> (N=16384)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": K1_DRAM_TRAFFIC_BYTES if T == FRAMES else None, "traffic_source": K1_TRAFFIC_SOURCE,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * samples_step, "kernel_ms": k1_ms,
-                         "other_kernels_ms": {"k_detect": prof.detect_ms / max(prof.detect_launches, 1), "k_window_query_total": prof.window_ms / args.steps,
-                                              "host_tracker": prof.tracker_host_ms / args.steps}},
+                         "other_kernels_ms": {"k_detect+list_ordering": k2_ms, "k_window_query_total": prof.window_ms / args.steps,
+                                              "host_tracker": prof.tracker_host_ms / args.steps},
+                         "k_detect": {"achieved": K2_ALG_BYTES_PER_SAMPLE * samples_step / (k2_ms / 1000.0) / 1e9, "unit": "GB/s",
+                                      "frac": K2_ALG_BYTES_PER_SAMPLE * samples_step / (k2_ms / 1000.0) / 1e9 / peak,
+                                      "cta_median_ms": prof.detect_cta_median_ms / max(prof.detect_launches, 1),
+                                      "cta_max_ms": prof.detect_cta_max_ms / max(prof.detect_launches, 1)}},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,

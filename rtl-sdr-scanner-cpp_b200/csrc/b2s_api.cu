@@ -1,5 +1,6 @@
 // b2s C-ABI implementation (include/b2s.h): engine / band objects, kernel launches, host tracker glue.
 // The compute path is CUDA only; there is deliberately no CPU fallback anywhere in this file.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -315,6 +316,29 @@ int validate_config(const b2s_band_config& c) {
 }
 
 }  // namespace
+
+// 2-D tensor map over a row-major fp32 matrix [rows][cols] with box [box_rows][box_cols] (cuTensorMapEncodeTiled through the
+// runtime's driver entry point: no link-time dependency on libcuda)
+static int make_tile_map(CUtensorMap* out, const float* base, size_t cols, size_t rows, int box_cols, int box_rows) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(B2S_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2S_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", static_cast<int>(r), box_cols, box_rows);
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // band

@@ -57,6 +57,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// 2-D tiled TMA load: the box described by the tensor map at coordinates (c0 = innermost, c1) -> shared memory; elements
+// outside the tensor are zero-filled and still counted in the mbarrier's transaction bytes.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+               "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ struct PushSlot {
   DevBuf<signed char> spec_rows;
   DevBuf<unsigned int> watch_max;
   DevBuf<unsigned long long> cta_ns;
+  CUtensorMap psd_map;  // PSD rows [max_frames][N] as a 2-D tensor, box = [32 frames][128 + 2*halo columns] (K2's tile)
   DevBuf<int> cand_flag;
   PinBuf<int> h_offsets, h_cand_flag;
   PinBuf<unsigned int> h_watch_max;
@@ -295,6 +296,10 @@ struct b2s_band : public DeviceQueries {
     for (int i = 0; i < n_slots; ++i) {
       PushSlot& s = slots[i];
       if ((rc = s.psd.alloc(static_cast<size_t>(max_frames) * n))) return rc;
+      {
+        const int hp = (c.grouping_x / 2 + 3) & ~3;
+        if ((rc = make_tile_map(&s.psd_map, s.psd.p, n, max_frames, kDetectBinsPerCta + 2 * hp, kDetectTileFrames))) return rc;
+      }
       if ((rc = s.peak_idx.alloc(max_frames))) return rc;
       if ((rc = s.peak_val.alloc(max_frames))) return rc;
       if ((rc = s.ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
@@ -573,9 +578,9 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     }
     if (profiling) CU(cudaEventRecord(s.ev[2], stream));
     if (half == 10 && Y == 21) {
-      k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da);
+      k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);
     } else {
-      k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da);
+      k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);
     }
     CU(cudaGetLastError());
     // order the per-frame slot lists by bin into one dense array
@@ -639,7 +644,8 @@ int b2s_band::finish_chunk(PushSlot& s) {
     if (s.cta_ns.p) {
       const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
       std::vector<unsigned long long> ns(2 * grid);
-      CU(cudaMemcpy(ns.data(), s.cta_ns.p, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpyAsync(ns.data(), s.cta_ns.p, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
       std::vector<double> dur(grid);
       for (int i = 0; i < grid; ++i) dur[i] = static_cast<double>(ns[2 * i + 1] - ns[2 * i]) * 1e-6;
       std::sort(dur.begin(), dur.end());
