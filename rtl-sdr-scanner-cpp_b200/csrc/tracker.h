@@ -39,6 +39,7 @@ struct TrackerParams {
 struct TrackedSignal {
   int64_t first = 0, last = 0;  // Signal::m_firstDataTime / m_lastDataTime
   float power = 0.0f;           // Signal::m_power
+  int watch = -1;               // slot of this key in the current chunk's watch list (refreshed by Tracker::run), -1 = none
 };
 
 // what the tracker may ask the device for (implemented by the band)
@@ -111,7 +112,10 @@ class Tracker {
       return -1;
     };
     int watched_alive = 0;
-    for (const auto& kv : signals) watched_alive += watch_slot(kv.first) >= 0 ? 1 : 0;
+    for (auto& kv : signals) {
+      kv.second.watch = watch_slot(kv.first);
+      watched_alive += kv.second.watch >= 0 ? 1 : 0;
+    }
     for (size_t t = 0; t < n_frames; ++t) {
       const int e0 = frame_begin[t], e1 = frame_begin[t + 1];
       const bool flags_valid = watch.flag != nullptr && watched_alive == watch.n;
@@ -140,7 +144,8 @@ class Tracker {
             int key = idx;
             const int rc = best_index(idx, static_cast<int>(t), dev, &key);
             if (rc != 0) return rc;
-            if (signals.insert({key, TrackedSignal{now, now, 0.0f}}).second && watch_slot(key) >= 0) watched_alive++;
+            const int slot = watch_slot(key);
+            if (signals.insert({key, TrackedSignal{now, now, 0.0f, slot}}).second && slot >= 0) watched_alive++;
           }
         }
       }
@@ -148,7 +153,7 @@ class Tracker {
       // ---- updateSignals: window maximum of the boxcar row around every key, then clearSignals ----
       for (auto it = signals.begin(); it != signals.end();) {
         TrackedSignal& s = it->second;
-        const int ws = watch_slot(it->first);
+        const int ws = s.watch;
         const unsigned int image = (ws >= 0 && watch.max) ? watch.max[t * kMaxWatch + ws] : 0u;
         if (image != 0u) {
           const float best = ordered_to_float(image);  // exact window maximum, also below the detection level
