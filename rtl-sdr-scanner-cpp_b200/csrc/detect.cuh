@@ -8,10 +8,10 @@
 //
 // Arithmetic contract: every float operation that feeds Averager state is the reference's operation in the reference's
 // order (separate sub / add / IEEE division, no FMA contraction) so m_sum, the ring and m_average are bit-identical.
-// The frequency boxcar is evaluated per aligned segment of 8 bins: the first bin's window is summed left to right, the
-// next 7 slide it exactly like the reference does (sum -= leaving; sum += entering), see boxcar_segment(). The
-// reference carries ONE running sum across the whole row (a 16384-long serial float chain); restarting it every
-// 8 bins changes rounding only (<= 1e-3 dB vs the reference's own drift, asserted in tests) and keeps the work
+// The frequency boxcar is evaluated per aligned segment of kBoxSegment (16) bins: the first bin's window is summed left to
+// right, the next 15 slide it exactly like the reference does (sum -= leaving; sum += entering), see boxcar_segment().
+// The reference carries ONE running sum across the whole row (a 16384-long serial float chain); restarting it every
+// 16 bins changes rounding only (<= 1e-3 dB vs the reference's own drift, asserted in tests) and keeps the work
 // parallel. b2s_average(..., exact=1) provides the serial form for operator-level bit parity.
 #pragma once
 #include <cstdio>
@@ -192,9 +192,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 // Warp roles of k_detect. One CTA owns kDetectBinsPerCta bins plus a halo of X/2 bins (rounded up to 4) on each side,
 // computed redundantly; every role walks the push in tiles of kDetectTileFrames frames and the roles meet only through
 // mbarriers, so each runs as far ahead as its buffers allow.
-#ifndef B2S_K2_DIV_IN_BOX
-#define B2S_K2_DIV_IN_BOX 0  // 1: steady tiles carry m_sum and the box lanes divide (more total work, shorter serial chain)
-#endif
 #ifndef B2S_K2_BOX_GROUPS
 #define B2S_K2_BOX_GROUPS 2
 #endif
@@ -220,10 +217,10 @@ constexpr int kBarFull = 2, kBarEmpty = 2 + kAvgBuffers;  // hardware barriers (
 //                  copies cap at ~17 GB/s per SM, measured); completion counted on an mbarrier (p_full), slots recycled
 //                  through p_empty.
 //   SUM warps      (thread = column) the only truly serial chain of the path: NoiseLearner subtraction and
-//                  m_sum -= leaving; m_sum += entering (averager.cpp:40-50), two dependent FADDs per frame. Nothing
-//                  else lives on this instruction stream: the last Y noise-subtracted values stay in registers from tile to
-//                  tile, and the running sums go to a transposed shared tile (s_full / s_empty).
-//   SPEC warps     (thread = owned bin) Spectrogram::process: the second serial chain (accumulation of raw rows).
+//                  m_sum -= leaving; m_sum += entering (averager.cpp:40-50), two dependent FADDs per frame. The last Y
+//                  noise-subtracted values stay in registers from tile to tile (never stored, never re-read);
+//                  m_average = m_sum / Y (off the chain) goes to a transposed shared tile (hardware barriers FULL / EMPTY
+//                  per buffer). The spectrogram accumulation (the second serial chain, spectrogram.cpp:46-49) rides along.
 //   BOX warps      (warp = 16-bin segment, lane = frame) boxcar over the averaged tile, threshold, watched-window maxima;
 //                  a lane with bins at or above the level reserves room in the frame's slot list with one global atomic
 //                  and writes its entries once the atomic has returned (after the watch block). Two groups of box
@@ -241,7 +238,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
   const int width = kDetectBinsPerCta + 2 * hp;     // columns held by this CTA (<= kSumThreads)
   const int tile_elems = TF * width;
   float* psd_tiles = sm;                            // [kDetectBuffers][TF][width] raw PSD rows (bulk-copy target)
-  // averaged values (m_average) handed to the box warps, TRANSPOSED: [2][width][kSumPitch] (column-major, pitch 33). The
+  // averaged values (m_average) handed to the box warps, TRANSPOSED: [kAvgBuffers][width][kSumPitch] (column-major, pitch 33). The
   // SUM thread of column c writes avg[c*33 + f] (lane stride 33: conflict-free); a box warp reads one column for 32
   // frames at once (lane = frame: consecutive words, conflict-free).
   constexpr int kSumPitch = TF + 1;
@@ -350,7 +347,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
               const float old = (f >= YC) ? q[f - YC] : lead[f];
               sum = __fsub_rn(sum, old);   // Averager::subtract, averager.cpp:46-50
               sum = __fadd_rn(sum, q[f]);  // Averager::add, averager.cpp:40-44
-              sum_col[f] = B2S_K2_DIV_IN_BOX ? sum : div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
+              sum_col[f] = div_const_fast<YC>(sum);  // m_average (t0 >= Y: the ring is full, averager.cpp:20-24); off the serial chain
             }
           };
           load_half(0);
@@ -494,10 +491,6 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           float w[SEG + 2 * H];
 #pragma unroll
           for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kSumPitch + f];  // columns outside [0, N) hold 0.0f
-          if (B2S_K2_DIV_IN_BOX && Y_T > 0 && tf == TF && t0 >= Y && (a.noise_samples + t0 >= a.learn_frames) && !dense) {  // a steady tile holds sums
-#pragma unroll
-            for (int i = 0; i < SEG + 2 * H; ++i) w[i] = div_const_fast<(Y_T > 0 ? Y_T : 1)>(w[i]);
-          }
           if (segment_interior(bin0, n, half)) {
             boxcar_segment<H>(w, box);
 #pragma unroll
