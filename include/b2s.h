@@ -199,6 +199,17 @@ int b2s_most_frequent_value(const int* data, int n);                            
 int b2s_learn_frames_from_ms(int64_t learning_ms, double frame_period_ms);                     /* NOISE_LEARNING_TIME -> frames */
 int b2s_decimator_factor(int32_t sample_rate_hz, int32_t fft_size);                            /* sdr_device.cpp:150-152 */
 
+
+/* ---- wire formats of the reference's MQTT payloads (network/data_controller.cpp:27-57), little-endian, packed ----
+ * so that rows / recordings produced here can be published to an unchanged sdr-hub. Both return 0 and the payload length in
+ * *written, or B2S_E_INVALID when `cap` is too small (then *written holds the required size).
+ * spectrogram ("sdr/<dev>/spectrogram"):        u64 time_ms, i32 start_hz, i32 stop_hz, i32 step_hz, u32 size, int8[size]
+ * transmission ("sdr/<dev>/transmission/uint8"): u64 time_ms, i32 start_hz, i32 stop_hz, u32 sample_rate, uint8 IQ pairs (int8 ^ 0x80) */
+int b2s_pack_spectrogram_message(int64_t time_ms, int32_t center_hz, int32_t sample_rate_hz, const int8_t* row, int size, uint8_t* out, size_t cap,
+                                 size_t* written); /* DataController::pushSpectrogram, data_controller.cpp:44-57 */
+int b2s_pack_transmission_message(int64_t time_ms, int32_t frequency_hz, int32_t sample_rate_hz, const int8_t* iq, int n_samples, uint8_t* out,
+                                  size_t cap, size_t* written); /* DataController::pushTransmission, data_controller.cpp:27-42 */
+
 #ifdef __cplusplus
 }
 #endif

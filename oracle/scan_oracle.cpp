@@ -613,6 +613,40 @@ int orc_most_frequent_value(const int* data, int n) {
 int orc_get_fft(int32_t sampleRate, int32_t maxStep) { return fftFor(sampleRate, maxStep); }
 int32_t orc_get_tuned_frequency(int32_t f, int32_t step) { return tuned(f, step); }
 
+// DataController::pushSpectrogram (network/data_controller.cpp:44-57): fields appended in order, native (little-endian) layout
+size_t orc_spectrogram_message(int64_t timeMs, int32_t frequency, int32_t sampleRate, const int8_t* data, int size, uint8_t* out) {
+  std::vector<uint8_t> bytes;
+  auto append = [&bytes](const void* p, size_t n) { bytes.insert(bytes.end(), static_cast<const uint8_t*>(p), static_cast<const uint8_t*>(p) + n); };
+  const uint64_t stamp = static_cast<uint64_t>(timeMs);
+  const int32_t start = frequency - sampleRate / 2, stop = frequency + sampleRate / 2, step = sampleRate / size;
+  const uint32_t count = static_cast<uint32_t>(size);
+  append(&stamp, 8);
+  append(&start, 4);
+  append(&stop, 4);
+  append(&step, 4);
+  append(&count, 4);
+  append(data, static_cast<size_t>(size));
+  std::memcpy(out, bytes.data(), bytes.size());
+  return bytes.size();
+}
+// DataController::pushTransmission (network/data_controller.cpp:27-42): header, then the int8 IQ bytes with the sign bit flipped
+size_t orc_transmission_message(int64_t timeMs, int32_t frequency, int32_t sampleRate, const int8_t* iq, int size, uint8_t* out) {
+  std::vector<uint8_t> bytes;
+  auto append = [&bytes](const void* p, size_t n) { bytes.insert(bytes.end(), static_cast<const uint8_t*>(p), static_cast<const uint8_t*>(p) + n); };
+  const uint64_t stamp = static_cast<uint64_t>(timeMs);
+  const int32_t start = frequency - sampleRate / 2, stop = frequency + sampleRate / 2;
+  const uint32_t rate = static_cast<uint32_t>(sampleRate);
+  append(&stamp, 8);
+  append(&start, 4);
+  append(&stop, 4);
+  append(&rate, 4);
+  const size_t header = bytes.size();
+  append(iq, 2 * static_cast<size_t>(size));
+  for (size_t i = header; i < bytes.size(); ++i) bytes[i] ^= 0x80;
+  std::memcpy(out, bytes.data(), bytes.size());
+  return bytes.size();
+}
+
 orc_averager* orc_averager_create(int size, int group) { return new orc_averager(size, group); }
 void orc_averager_destroy(orc_averager* a) { delete a; }
 void orc_averager_push(orc_averager* a, const float* d) { a->impl.push(d); }

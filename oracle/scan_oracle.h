@@ -96,6 +96,10 @@ int orc_most_frequent_value(const int* data, int n);                          /*
 int orc_get_fft(int32_t sample_rate, int32_t max_step);                       /* radio_utils.cpp:98-104 */
 int32_t orc_get_tuned_frequency(int32_t f, int32_t step);                     /* radio_utils.cpp:86-96 */
 
+/* MQTT payload layouts, network/data_controller.cpp:27-57; return the number of bytes written into out (sized by the caller) */
+size_t orc_spectrogram_message(int64_t time_ms, int32_t frequency, int32_t sample_rate, const int8_t* data, int size, uint8_t* out);
+size_t orc_transmission_message(int64_t time_ms, int32_t frequency, int32_t sample_rate, const int8_t* iq, int size, uint8_t* out);
+
 typedef struct orc_averager orc_averager;
 orc_averager* orc_averager_create(int size, int group_size);
 void orc_averager_destroy(orc_averager* a);

@@ -205,6 +205,8 @@ def lib():
         L.b2s_contains_with_margin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.b2s_most_frequent_value.argtypes = [C.c_void_p, C.c_int]
         L.b2s_learn_frames_from_ms.argtypes = [C.c_int64, C.c_double]
+        for f in ("b2s_pack_spectrogram_message", "b2s_pack_transmission_message"):
+            getattr(L, f).argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.b2s_default_config.argtypes = [C.POINTER(BandConfig), C.c_int32, C.c_int32, C.c_int32]
         L.b2s_default_config.restype = None
         _lib = L
@@ -453,6 +455,25 @@ def get_fft(sample_rate_hz: int, max_step_hz: int) -> int:
 
 def get_tuned_frequency(f: int, step: int) -> int:
     return lib().b2s_get_tuned_frequency(f, step)
+
+
+def _pack(fn, time_ms: int, frequency_hz: int, sample_rate_hz: int, data: np.ndarray, count: int, header: int) -> bytes:
+    x = np.ascontiguousarray(data, dtype=np.int8)
+    out = np.empty(header + x.size, dtype=np.uint8)
+    written = C.c_size_t(0)
+    _check(fn(time_ms, frequency_hz, sample_rate_hz, _ptr(x), count, _ptr(out), out.size, C.byref(written)))
+    return out[: written.value].tobytes()
+
+
+def pack_spectrogram_message(time_ms: int, center_hz: int, sample_rate_hz: int, row: np.ndarray) -> bytes:
+    """DataController::pushSpectrogram payload (data_controller.cpp:44-57) for one int8 spectrogram row."""
+    return _pack(lib().b2s_pack_spectrogram_message, time_ms, center_hz, sample_rate_hz, row, int(np.asarray(row).size), 24)
+
+
+def pack_transmission_message(time_ms: int, frequency_hz: int, sample_rate_hz: int, iq_int8_pairs: np.ndarray) -> bytes:
+    """DataController::pushTransmission payload (data_controller.cpp:27-42) for interleaved int8 I/Q samples."""
+    x = np.asarray(iq_int8_pairs)
+    return _pack(lib().b2s_pack_transmission_message, time_ms, frequency_hz, sample_rate_hz, x, int(x.size // 2), 20)
 
 
 def get_max_index(data: np.ndarray, index: int, group_size: int) -> int:

@@ -853,4 +853,47 @@ int b2s_learn_frames_from_ms(int64_t learning_ms, double frame_period_ms) {
 }
 int b2s_decimator_factor(int32_t sample_rate_hz, int32_t fft_size) { return host::decimator_factor(sample_rate_hz, fft_size); }
 
+// append the object representation of a field (the reference writes through reinterpret_cast on a little-endian host)
+static void put_bytes(uint8_t* out, size_t& at, const void* v, size_t n) {
+  std::memcpy(out + at, v, n);
+  at += n;
+}
+#define B2S_PUT(type, expr)          \
+  do {                               \
+    const type field_ = (expr);      \
+    put_bytes(out, at, &field_, sizeof(type)); \
+  } while (0)
+
+int b2s_pack_spectrogram_message(int64_t time_ms, int32_t center_hz, int32_t sample_rate_hz, const int8_t* row, int size, uint8_t* out, size_t cap,
+                                 size_t* written) {
+  if (!row || !out || !written || size <= 0) return fail(B2S_E_INVALID, "b2s_pack_spectrogram_message: NULL argument or size <= 0");
+  const size_t need = sizeof(uint64_t) + 3 * sizeof(int32_t) + sizeof(uint32_t) + static_cast<size_t>(size);
+  *written = need;
+  if (cap < need) return fail(B2S_E_INVALID, "spectrogram message needs %zu bytes, buffer holds %zu", need, cap);
+  size_t at = 0;
+  B2S_PUT(uint64_t, time_ms);
+  B2S_PUT(int32_t, center_hz - sample_rate_hz / 2);  // start
+  B2S_PUT(int32_t, center_hz + sample_rate_hz / 2);  // stop
+  B2S_PUT(int32_t, sample_rate_hz / size);           // step
+  B2S_PUT(uint32_t, size);
+  std::memcpy(out + at, row, static_cast<size_t>(size));
+  return 0;
+}
+
+int b2s_pack_transmission_message(int64_t time_ms, int32_t frequency_hz, int32_t sample_rate_hz, const int8_t* iq, int n_samples, uint8_t* out,
+                                  size_t cap, size_t* written) {
+  if (!out || !written || n_samples < 0 || (n_samples > 0 && !iq)) return fail(B2S_E_INVALID, "b2s_pack_transmission_message: bad argument");
+  const size_t header = sizeof(uint64_t) + 2 * sizeof(int32_t) + sizeof(uint32_t), body = 2 * static_cast<size_t>(n_samples);
+  *written = header + body;
+  if (cap < header + body) return fail(B2S_E_INVALID, "transmission message needs %zu bytes, buffer holds %zu", header + body, cap);
+  size_t at = 0;
+  B2S_PUT(uint64_t, time_ms);
+  B2S_PUT(int32_t, frequency_hz - sample_rate_hz / 2);
+  B2S_PUT(int32_t, frequency_hz + sample_rate_hz / 2);
+  B2S_PUT(uint32_t, sample_rate_hz);
+  for (size_t i = 0; i < body; ++i) out[at + i] = static_cast<uint8_t>(iq[i]) ^ 0x80u;  // offset-binary bytes, data_controller.cpp:38-40
+  return 0;
+}
+#undef B2S_PUT
+
 }  // extern "C"

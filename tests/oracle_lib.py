@@ -63,6 +63,9 @@ def oracle():
         L.orc_contains_with_margin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.orc_most_frequent_value.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_tuned_frequency.restype = C.c_int32
+        for f in ("orc_spectrogram_message", "orc_transmission_message"):
+            getattr(L, f).restype = C.c_size_t
+            getattr(L, f).argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_averager_create.restype = C.c_void_p
         L.orc_averager_create.argtypes = [C.c_int, C.c_int]
         for f in ("destroy", "reset"):

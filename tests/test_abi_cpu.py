@@ -84,6 +84,44 @@ def test_host_helpers_match_oracle_on_random_inputs():
         assert b2s.get_tuned_frequency(f, step) == O.orc_get_tuned_frequency(f, step)
 
 
+def test_wire_messages_match_the_reference_layout():
+    """MQTT payloads of DataController (network/data_controller.cpp:27-57): an independent struct.pack statement of the
+    layout, the oracle restatement and the library agree byte for byte; short buffers are refused with the needed size."""
+    import struct
+
+    import oracle_lib as ol
+
+    rng = np.random.default_rng(5)
+    O = ol.oracle()
+    for size in (1, 7, 256, 8192):
+        t_ms = int(rng.integers(1, 2**40))
+        f = int(rng.integers(50_000_000, 1_500_000_000))
+        fs = int(rng.choice([2_048_000, 20_000_000, 40_000_000]))
+        row = rng.integers(-128, 128, size).astype(np.int8)
+        want = struct.pack("<Qiii", t_ms, f - fs // 2, f + fs // 2, fs // size) + struct.pack("<I", size) + row.tobytes()
+        assert b2s.pack_spectrogram_message(t_ms, f, fs, row) == want
+        buf = np.empty(24 + size, dtype=np.uint8)
+        n = O.orc_spectrogram_message(t_ms, f, fs, row.ctypes.data_as(C.c_void_p), size, buf.ctypes.data_as(C.c_void_p))
+        assert buf[:n].tobytes() == want
+
+        iq = rng.integers(-128, 128, 2 * size).astype(np.int8)
+        want = struct.pack("<QiiI", t_ms, f - fs // 2, f + fs // 2, fs) + (iq.view(np.uint8) ^ 0x80).tobytes()
+        assert b2s.pack_transmission_message(t_ms, f, fs, iq) == want
+        buf = np.empty(20 + 2 * size, dtype=np.uint8)
+        n = O.orc_transmission_message(t_ms, f, fs, iq.ctypes.data_as(C.c_void_p), size, buf.ctypes.data_as(C.c_void_p))
+        assert buf[:n].tobytes() == want
+    # the extremes of int8 map to 0x00 / 0xff / 0x80 (offset binary), as the sdr-hub decoder expects
+    edge = np.array([-128, 127, 0, -1], dtype=np.int8)
+    assert b2s.pack_transmission_message(0, 0, 0, edge)[20:] == bytes([0x00, 0xFF, 0x80, 0x7F])
+    lib = C.CDLL(b2s.LIB_PATH)
+    lib.b2s_pack_spectrogram_message.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    need = C.c_size_t(0)
+    row = np.zeros(100, dtype=np.int8)
+    small = np.zeros(10, dtype=np.uint8)
+    assert lib.b2s_pack_spectrogram_message(1, 2, 3, row.ctypes.data_as(C.c_void_p), 100, small.ctypes.data_as(C.c_void_p), 10, C.byref(need)) != 0
+    assert need.value == 124
+
+
 def test_default_config_follows_setup_chains():
     """sdr_device.cpp:148-152 + config.h:24-38 for the two sample rates the reference's tests use."""
     cfg = b2s.BandConfig()
