@@ -157,7 +157,7 @@ typedef struct b2s_profile {
   /* load balance of K2 (one CTA per 128 bins): per-CTA run time in ms, median and slowest, summed over launches */
   double detect_cta_median_ms, detect_cta_max_ms;
 } b2s_profile;
-int b2s_band_set_profiling(b2s_band* b, int enable);
+int b2s_band_set_profiling(b2s_band* b, int enable); /* 0 off, 1 kernel times and byte counts, 2 also K2 per-CTA run times */
 int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset);
 
 /* ---- side channels ---- */

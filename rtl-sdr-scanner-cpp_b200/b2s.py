@@ -387,8 +387,9 @@ class Band:
         out.n_spectrogram_rows = res.n_spectrogram_rows
         return out
 
-    def set_profiling(self, enable: bool = True):
-        _check(lib().b2s_band_set_profiling(self._h, 1 if enable else 0))
+    def set_profiling(self, enable=True):
+        """False/0 = off, True/1 = kernel times and byte counts, 2 = also the per-CTA run times of K2."""
+        _check(lib().b2s_band_set_profiling(self._h, int(enable)))
 
     def get_profile(self, reset: bool = True) -> Profile:
         p = Profile()

@@ -577,6 +577,7 @@ int b2s_band_set_profiling(b2s_band* b, int enable) {
   int rc = b->drain();
   if (rc) return rc;
   b->profiling = enable != 0;
+  b->profile_ctas = enable >= 2;
   return 0;
 }
 int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset) {

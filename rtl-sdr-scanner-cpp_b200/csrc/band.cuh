@@ -113,6 +113,7 @@ struct b2s_band : public DeviceQueries {
 
   // profiling
   bool profiling = false;
+  bool profile_ctas = false;  // level 2: also per-CTA run times of K2 (one small D2H + sort per push)
   b2s_profile prof{};
 
   // worker (async mode)
@@ -552,7 +553,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   }
   da.spec_rows = s.spec_rows.p;
   da.cta_ns = nullptr;
-  if (profiling) {
+  if (profiling && profile_ctas) {
     if ((rc = s.cta_ns.alloc(2 * ((n + kDetectBinsPerCta - 1) / kDetectBinsPerCta)))) return rc;
     da.cta_ns = s.cta_ns.p;
   }
@@ -641,7 +642,7 @@ int b2s_band::finish_chunk(PushSlot& s) {
     prof.spectral_ms += ms;
     CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
     prof.detect_ms += ms;
-    if (s.cta_ns.p) {
+    if (profile_ctas && s.cta_ns.p) {
       const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
       std::vector<unsigned long long> ns(2 * grid);
       CU(cudaMemcpyAsync(ns.data(), s.cta_ns.p, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost, st));
