@@ -5,8 +5,8 @@
 //   sources/radio/averager.cpp, sources/utils/utils.cpp, sources/utils/radio_utils.cpp, sources/logger.cpp
 //   + header-only sources/utils/collection_utils.h
 // It lets pytest pin the CPU restatement in oracle/scan_oracle.cpp against the real reference code for every
-// piece of the hot path that is buildable here. The GNU Radio blocks (PSD, NoiseLearner,
-// Transmission, Spectrogram) cannot be built (GNU Radio/FFTW/VOLK/SoapySDR are absent), so they are restated only.
+// piece of the hot path that is buildable here. The reference's block objects (PSD, NoiseLearner,
+// Transmission, Spectrogram, DataController) are driven by oracle/ref_blocks_shim.cpp, which lives in the same library.
 #include <logger.h>
 #include <radio/averager.h>
 #include <utils/collection_utils.h>

@@ -14,6 +14,14 @@
 #include <unordered_map>
 #include <vector>
 
+// sources/radio/blocks/psd.cpp:18-20, all fp32: 10 * log10(|z|^2 / fs); `lin` (optional) receives |z|^2 / fs
+static inline float psdDb(std::complex<float> z, float fs, float* lin) {
+  const float mag = std::abs(z);
+  const float pw = std::pow(mag, 2.0f) / fs;
+  if (lin) *lin = pw;
+  return 10.0f * std::log10(pw);
+}
+
 namespace {
 
 constexpr float kNoData = -100.0f;  // setNoData, sources/utils/radio_utils.cpp:72-76
@@ -381,11 +389,7 @@ struct orc_chain {
       } else {
         z = std::complex<float>(static_cast<float>(work64[k].real()), static_cast<float>(work64[k].imag()));
       }
-      // sources/radio/blocks/psd.cpp:18-20, all fp32
-      const float mag = std::abs(z);
-      const float pw = std::pow(mag, 2.0f) / fs;
-      out[j] = 10.0f * std::log10(pw);
-      if (lin) lin[j] = pw;
+      out[j] = psdDb(z, fs, lin ? &lin[j] : nullptr);
     }
   }
 
@@ -645,6 +649,12 @@ size_t orc_transmission_message(int64_t timeMs, int32_t frequency, int32_t sampl
   for (size_t i = header; i < bytes.size(); ++i) bytes[i] ^= 0x80;
   std::memcpy(out, bytes.data(), bytes.size());
   return bytes.size();
+}
+
+// PSD::work (psd.cpp:11-22) on `items` vectors of n complex values (no shift: fft_v does that)
+void orc_psd_from_spectrum(int n, int32_t sampleRate, const float* x, float* out, int items) {
+  const float fs = static_cast<float>(sampleRate);
+  for (int i = 0; i < n * items; ++i) out[i] = psdDb(std::complex<float>(x[2 * i], x[2 * i + 1]), fs, nullptr);
 }
 
 orc_averager* orc_averager_create(int size, int group) { return new orc_averager(size, group); }

@@ -10,10 +10,15 @@
  *   - Averager, average(), getMaxIndex, containsWithMargin, mostFrequentValue, getFft, getTunedFrequency,
  *     setNoData: PINNED against the reference's own gtest vectors (tests/golden/) and against the reference's
  *     own objects compiled from /root/reference into oracle/_ref/libref.so (oracle/Makefile).
- *   - window, FFT, fftshift, PSD formula, NoiseLearner, Transmission/Signal, Spectrogram: the reference has no
- *     test or fixture for them and the GNU Radio / FFTW sources are not under /root/reference => PARITY UNPINNED
- *     for these pieces; they follow the reference source line by line (cited per function) and the documented
- *     GNU Radio 3.10 behaviour, cross-checked against numpy.fft and scripts/converter.py:17-21 semantics.
+ *   - PSD::work, NoiseLearner::work, Transmission::work (+ Signal), Spectrogram::work, DataController payloads: PINNED
+ *     against the reference's own block objects — sources/radio/blocks/{psd,noise_learner,transmission,spectrogram}.cpp,
+ *     sources/radio/signal.cpp, sources/network/data_controller.cpp compiled UNMODIFIED into oracle/_ref/libref.so behind
+ *     name-only stand-ins for the absent GNU Radio / Paho headers and an injected clock (oracle/ref_blocks_shim.cpp);
+ *     tests/test_oracle_vs_reference_blocks.py drives both with the same PSD rows, frame by frame: rows bit for bit,
+ *     transmission lists and published payloads identical.
+ *   - window, FFT, fftshift (gr::fft::fft_v = GNU Radio + FFTW, not under /root/reference): PARITY UNPINNED for these
+ *     pieces; they follow the documented GNU Radio 3.10 behaviour, cross-checked against numpy.fft, closed-form known
+ *     answers and scripts/converter.py:17-21 semantics.
  */
 #pragma once
 #include <stddef.h>
@@ -89,6 +94,7 @@ void orc_hamming(int n, float* w);
 void orc_fft_f64(int n, const float* in_interleaved, float* out_interleaved); /* unnormalised forward DFT, fp64 inside */
 void orc_fft_f32(int n, const float* in_interleaved, float* out_interleaved); /* same in fp32 (timed baseline) */
 void orc_psd_frame(const orc_config* cfg, const float* window, const void* iq_frame, float* psd_db, float* power_lin);
+void orc_psd_from_spectrum(int n, int32_t sample_rate, const float* x_interleaved, float* out, int items); /* PSD::work, psd.cpp:11-22 */
 void orc_average(const float* in, float* out, int size, int group_size);      /* utils.cpp:31-53 */
 int orc_get_max_index(const float* data, int size, int index, int group_size); /* collection_utils.h:9-14 */
 int orc_contains_with_margin(const int* keys, int n_keys, int index, int margin, int* found); /* collection_utils.h:17-27 */

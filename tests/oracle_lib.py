@@ -102,12 +102,77 @@ def ref():
         L.ref_get_tuned_frequency.restype = C.c_int32
         L.ref_split_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.ref_get_resamplers_factors.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        # the reference's own BLOCK objects (oracle/ref_blocks_shim.cpp): PSD, NoiseLearner, Transmission, Spectrogram, DataController
+        if hasattr(L, "ref_chain_create"):
+            L.ref_set_time.argtypes = [C.c_int64]
+            L.ref_psd_work.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+            L.ref_chain_create.restype = C.c_void_p
+            L.ref_chain_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int64]
+            L.ref_chain_destroy.argtypes = [C.c_void_p]
+            L.ref_chain_reset.argtypes = [C.c_void_p]
+            L.ref_chain_set_center.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+            L.ref_chain_push_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.ref_published_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_int]
+            L.ref_push_spectrogram.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+            L.ref_push_transmission.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int]
         _ref = L
     return _ref
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def have_ref_blocks() -> bool:
+    return have_ref() and hasattr(ref(), "ref_chain_create")
+
+
+class RefBlocksChain:
+    """psd -> NoiseLearner -> Transmission (+ psd -> Spectrogram -> DataController) built from the REFERENCE's own compiled
+    objects, wired like SdrDevice::setupChains (sdr_device.cpp:147-171) and driven one PSD row at a time with an injected clock."""
+
+    def __init__(self, cfg: BandConfig, t0_ms: int, bandwidth_hz: int, with_spectrogram: bool = True):
+        import json
+
+        self.cfg, self.L = cfg, ref()
+        ignored = [[int(cfg.ignored_lo_hz[i]), int(cfg.ignored_hi_hz[i])] for i in range(cfg.n_ignored)]
+        text = json.dumps({"ignored": ignored, "bandwidth": int(bandwidth_hz), "min_time_ms": int(cfg.min_time_ms), "timeout_ms": int(cfg.timeout_ms),
+                           "tuning_step": int(cfg.tuning_step_hz)})
+        self.h = C.c_void_p(self.L.ref_chain_create(text.encode(), cfg.fft_size, cfg.sample_rate_hz, cfg.center_hz, cfg.range_lo_hz, cfg.range_hi_hz,
+                                                    cfg.group_size_bins, cfg.start_level, cfg.stop_level, 1 if with_spectrogram else 0, t0_ms))
+        self.L.ref_published_clear()
+
+    def push_row(self, psd_row, now_ms):
+        n = self.cfg.fft_size
+        row = np.ascontiguousarray(psd_row, dtype=np.float32)
+        q = np.empty(n, dtype=np.float32)
+        freq = np.zeros(MAX_TX, dtype=np.int32)
+        flush = np.zeros(MAX_TX, dtype=np.int32)
+        k = self.L.ref_chain_push_row(self.h, _p(row), int(now_ms), _p(q), _p(freq), _p(flush), MAX_TX)
+        return q, [(int(freq[i]), int(flush[i])) for i in range(min(k, MAX_TX))]
+
+    def reset(self):
+        self.L.ref_chain_reset(self.h)
+
+    def set_center(self, c, lo, hi):
+        self.L.ref_chain_set_center(self.h, c, lo, hi)
+
+    def published(self, clear=True):
+        out = []
+        for i in range(self.L.ref_published_count()):
+            topic = C.create_string_buffer(128)
+            buf = np.empty(1 << 16, dtype=np.uint8)
+            k = self.L.ref_published_get(i, topic, 128, _p(buf), buf.size)
+            out.append((topic.value.decode(), buf[:k].tobytes()))
+        if clear:
+            self.L.ref_published_clear()
+        return out
+
+    def __del__(self):
+        try:
+            self.L.ref_chain_destroy(self.h)
+        except Exception:
+            pass
 
 
 class CpuAverager:
