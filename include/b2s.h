@@ -200,6 +200,21 @@ int b2s_learn_frames_from_ms(int64_t learning_ms, double frame_period_ms);      
 int b2s_decimator_factor(int32_t sample_rate_hz, int32_t fft_size);                            /* sdr_device.cpp:150-152 */
 
 
+/* ---- Transmission bookkeeping on HOST rows (operator-level parity with transmission.cpp:57-176; no GPU involved) ----
+ * The same host tracker that follows K2's detection entries inside b2s_band_push, fed from dense rows instead:
+ * box_rows[n_frames][N] = average(Averager::average(), GROUPING_X) and q_rows[n_frames][N] = the NoiseLearner output rows
+ * (the Averager ring that getBestIndex votes on). Frames are stamped like b2s_band_push stamps them. With use_watch != 0 the
+ * per-frame window maxima / candidate flags that K2 reports for the live keys are emulated as well (the path the band
+ * takes in steady state); the lists must not depend on it. tx_count[n_frames], tx[n_frames][B2S_MAX_TX] (either may be
+ * NULL). State (signal map, last Y rows of q) carries over between calls. */
+typedef struct b2s_host_transmission b2s_host_transmission;
+int b2s_host_transmission_create(const b2s_band_config* cfg, b2s_host_transmission** out);
+int b2s_host_transmission_destroy(b2s_host_transmission* h);
+int b2s_host_transmission_reset(b2s_host_transmission* h); /* Transmission::resetBuffers: drop the signals and the ring */
+double b2s_host_transmission_last_run_ms(b2s_host_transmission* h); /* wall time of the bookkeeping of the last push (measurement) */
+int b2s_host_transmission_push(b2s_host_transmission* h, const float* box_rows, const float* q_rows, int n_frames, int64_t t0_ms,
+                               double frame_period_ms, int use_watch, int32_t* tx_count, b2s_transmission* tx);
+
 /* ---- wire formats of the reference's MQTT payloads (network/data_controller.cpp:27-57), little-endian, packed ----
  * so that rows / recordings produced here can be published to an unchanged sdr-hub. Both return 0 and the payload length in
  * *written, or B2S_E_INVALID when `cap` is too small (then *written holds the required size).

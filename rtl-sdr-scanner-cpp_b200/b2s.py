@@ -205,6 +205,12 @@ def lib():
         L.b2s_contains_with_margin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.b2s_most_frequent_value.argtypes = [C.c_void_p, C.c_int]
         L.b2s_learn_frames_from_ms.argtypes = [C.c_int64, C.c_double]
+        L.b2s_host_transmission_create.argtypes = [C.POINTER(BandConfig), C.POINTER(C.c_void_p)]
+        L.b2s_host_transmission_destroy.argtypes = [C.c_void_p]
+        L.b2s_host_transmission_reset.argtypes = [C.c_void_p]
+        L.b2s_host_transmission_last_run_ms.argtypes = [C.c_void_p]
+        L.b2s_host_transmission_last_run_ms.restype = C.c_double
+        L.b2s_host_transmission_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         for f in ("b2s_pack_spectrogram_message", "b2s_pack_transmission_message"):
             getattr(L, f).argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.b2s_default_config.argtypes = [C.POINTER(BandConfig), C.c_int32, C.c_int32, C.c_int32]
@@ -456,6 +462,45 @@ def get_fft(sample_rate_hz: int, max_step_hz: int) -> int:
 
 def get_tuned_frequency(f: int, step: int) -> int:
     return lib().b2s_get_tuned_frequency(f, step)
+
+
+class HostTransmission:
+    """Transmission bookkeeping on host rows (b2s_host_transmission_*): the band's tracker without the GPU. push() returns,
+    per frame, the list of (shift_hz, flush, key, power) exactly as Transmission::getSortedTransmissions orders it."""
+
+    def __init__(self, cfg: BandConfig):
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(lib().b2s_host_transmission_create(C.byref(cfg), C.byref(self._h)))
+
+    def push(self, box_rows: np.ndarray, q_rows: np.ndarray, t0_ms: int, frame_period_ms: float, use_watch: bool = True):
+        box = np.ascontiguousarray(box_rows, dtype=np.float32)
+        q = np.ascontiguousarray(q_rows, dtype=np.float32)
+        frames = box.shape[0]
+        assert box.shape == q.shape == (frames, self.cfg.fft_size)
+        count = np.zeros(frames, dtype=np.int32)
+        tx = (Transmission * (frames * MAX_TX))()
+        _check(lib().b2s_host_transmission_push(self._h, _ptr(box), _ptr(q), frames, int(t0_ms), float(frame_period_ms), 1 if use_watch else 0, _ptr(count),
+                                               C.cast(tx, C.c_void_p)))
+        return [[(tx[k * MAX_TX + i].shift_hz, tx[k * MAX_TX + i].flush, tx[k * MAX_TX + i].key, tx[k * MAX_TX + i].power) for i in range(min(int(count[k]), MAX_TX))]
+                for k in range(frames)]
+
+    def last_run_ms(self) -> float:
+        return lib().b2s_host_transmission_last_run_ms(self._h)
+
+    def reset(self):
+        _check(lib().b2s_host_transmission_reset(self._h))
+
+    def close(self):
+        if self._h:
+            lib().b2s_host_transmission_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _pack(fn, time_ms: int, frequency_hz: int, sample_rate_hz: int, data: np.ndarray, count: int, header: int) -> bytes:

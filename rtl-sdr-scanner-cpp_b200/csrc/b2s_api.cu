@@ -854,6 +854,168 @@ int b2s_learn_frames_from_ms(int64_t learning_ms, double frame_period_ms) {
 }
 int b2s_decimator_factor(int32_t sample_rate_hz, int32_t fft_size) { return host::decimator_factor(sample_rate_hz, fft_size); }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Transmission bookkeeping on host rows: the band's tracker behind a DeviceQueries that reads dense host arrays
+// ------------------------------------------------------------------------------------------------------------
+struct b2s_host_transmission : DeviceQueries {
+  b2s_band_config cfg{};
+  Tracker tracker;
+  std::vector<float> history;  // the last Y rows of q before the current call, oldest -> newest (zeros before any data)
+  // current call
+  const float* box = nullptr;
+  const float* q = nullptr;
+  int frames = 0;
+  double last_run_ms = 0.0;  // wall time of the last Tracker::run (the bookkeeping alone, without building its inputs)
+
+  int fetch_ring_window(int frame_first, int rows, int bin_lo, int width, float* out) override {
+    const int n = cfg.fft_size, Y = cfg.grouping_y;
+    for (int r = 0; r < rows; ++r) {
+      const int f = frame_first + r;
+      float* dst = out + static_cast<size_t>(r) * width;
+      const float* src = nullptr;
+      if (f >= 0) {
+        src = q + static_cast<size_t>(f) * n;
+      } else if (Y + f >= 0) {
+        src = history.data() + static_cast<size_t>(Y + f) * n;  // f = -1 is the newest row of the previous call
+      }
+      for (int i = 0; i < width; ++i) dst[i] = src ? src[bin_lo + i] : 0.0f;
+    }
+    return 0;
+  }
+  int query_windows(const std::vector<Window>& w, std::vector<std::vector<float>>& values, std::vector<std::vector<int>>& indices) override {
+    const int n = cfg.fft_size;
+    values.assign(w.size(), {});
+    indices.assign(w.size(), {});
+    for (size_t i = 0; i < w.size(); ++i) {
+      for (int f = w[i].frame_lo; f < w[i].frame_hi; ++f) {
+        const float* row = box + static_cast<size_t>(f) * n;
+        int best = w[i].bin_lo;
+        for (int b = w[i].bin_lo + 1; b <= w[i].bin_hi; ++b) {
+          if (row[best] < row[b]) best = b;  // first maximum, collection_utils.h:9-14
+        }
+        values[i].push_back(row[best]);
+        indices[i].push_back(best);
+      }
+    }
+    return 0;
+  }
+};
+
+extern "C" {
+
+int b2s_host_transmission_create(const b2s_band_config* cfg, b2s_host_transmission** out) {
+  if (!cfg || !out) return fail(B2S_E_INVALID, "NULL argument");
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  auto* h = new b2s_host_transmission();
+  h->cfg = *cfg;
+  h->cfg.window_taps = nullptr;
+  TrackerParams& p = h->tracker.p;
+  p.n = cfg->fft_size;
+  p.sample_rate = cfg->sample_rate_hz;
+  p.center = cfg->center_hz;
+  p.range_lo = cfg->range_lo_hz;
+  p.range_hi = cfg->range_hi_hz;
+  p.n_ignored = cfg->n_ignored;
+  for (int i = 0; i < cfg->n_ignored; ++i) {
+    p.ignored_lo[i] = cfg->ignored_lo_hz[i];
+    p.ignored_hi[i] = cfg->ignored_hi_hz[i];
+  }
+  p.group_size = cfg->group_size_bins;
+  p.group_y = cfg->grouping_y;
+  p.start_level = cfg->start_level;
+  p.stop_level = cfg->stop_level;
+  p.tuning_step = cfg->tuning_step_hz;
+  p.min_time = cfg->min_time_ms;
+  p.timeout = cfg->timeout_ms;
+  p.max_time = cfg->max_time_ms;
+  h->history.assign(static_cast<size_t>(cfg->grouping_y) * cfg->fft_size, 0.0f);  // Averager::reset fills the ring with zeros
+  *out = h;
+  return 0;
+}
+int b2s_host_transmission_destroy(b2s_host_transmission* h) {
+  delete h;
+  return 0;
+}
+double b2s_host_transmission_last_run_ms(b2s_host_transmission* h) { return h ? h->last_run_ms : 0.0; }
+int b2s_host_transmission_reset(b2s_host_transmission* h) {
+  if (!h) return fail(B2S_E_INVALID, "NULL handle");
+  h->tracker.reset();
+  std::fill(h->history.begin(), h->history.end(), 0.0f);
+  return 0;
+}
+int b2s_host_transmission_push(b2s_host_transmission* h, const float* box_rows, const float* q_rows, int n_frames, int64_t t0_ms,
+                               double frame_period_ms, int use_watch, int32_t* tx_count, b2s_transmission* tx) {
+  if (!h || !box_rows || !q_rows || n_frames < 0) return fail(B2S_E_INVALID, "b2s_host_transmission_push: bad argument");
+  const int n = h->cfg.fft_size, Y = h->cfg.grouping_y, T = n_frames;
+  const TrackerParams& p = h->tracker.p;
+  h->box = box_rows;
+  h->q = q_rows;
+  h->frames = T;
+  // what K2 hands to the tracker: per frame the bins at or above min(start, stop), ascending
+  const float level = std::min(p.start_level, p.stop_level);
+  std::vector<DetectEntry> entries;
+  std::vector<int> begin(T + 1, 0);
+  for (int t = 0; t < T; ++t) {
+    const float* row = box_rows + static_cast<size_t>(t) * n;
+    begin[t] = static_cast<int>(entries.size());
+    for (int b = 0; b < n; ++b) {
+      if (row[b] >= level) entries.push_back(DetectEntry{b, row[b]});
+    }
+  }
+  begin[T] = static_cast<int>(entries.size());
+  // ... and, for the keys alive when the call starts, the window maxima and the "uncovered candidate" flags (k_detect's box warps)
+  Tracker::Watch watch;
+  std::vector<int> keys, flags;
+  std::vector<unsigned int> maxima;
+  if (use_watch) {
+    for (const auto& kv : h->tracker.signals) {
+      if (static_cast<int>(keys.size()) < kMaxWatch) keys.push_back(kv.first);
+    }
+    const int gh = p.group_size / 2, margin = (p.group_size % 2 == 0) ? gh : gh + 1;
+    maxima.assign(static_cast<size_t>(T) * kMaxWatch, 0u);
+    flags.assign(T, 0);
+    for (int t = 0; t < T; ++t) {
+      const float* row = box_rows + static_cast<size_t>(t) * n;
+      for (size_t i = 0; i < keys.size(); ++i) {
+        float m = -INFINITY;
+        for (int b = std::max(0, keys[i] - gh); b <= std::min(n - 1, keys[i] + gh); ++b) m = std::max(m, row[b]);
+        maxima[static_cast<size_t>(t) * kMaxWatch + i] = float_to_ordered(m);
+      }
+      for (int b = 0; b < n && !flags[t]; ++b) {
+        if (row[b] < p.start_level) continue;
+        bool covered = false;
+        for (int key : keys) covered = covered || (b >= key - margin && b <= key + margin);
+        if (!covered) flags[t] = 1;
+      }
+    }
+    watch = Tracker::Watch{static_cast<int>(keys.size()), keys.data(), maxima.data(), flags.data()};
+  }
+  std::vector<Tracker::FrameState> states;
+  const DetectEntry* ep = entries.empty() ? nullptr : entries.data();
+  const auto run_t0 = std::chrono::steady_clock::now();
+  int rc = h->tracker.run(ep, begin.data(), static_cast<size_t>(T), t0_ms, frame_period_ms, 0, *h, tx_count != nullptr || tx != nullptr, watch, states);
+  h->last_run_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - run_t0).count();
+  if (rc) return rc;
+  if (tx_count) std::fill(tx_count, tx_count + T, 0);
+  for (const auto& fs : states) {
+    const int total = h->tracker.sorted_transmissions(fs, tx ? tx + static_cast<size_t>(fs.frame) * B2S_MAX_TX : nullptr, tx ? B2S_MAX_TX : 0);
+    if (tx_count) tx_count[fs.frame] = total;
+  }
+  // keep the newest Y rows of q for the next call's getBestIndex look-back
+  std::vector<float> next(static_cast<size_t>(Y) * n);
+  for (int i = 0; i < Y; ++i) {
+    const int f = T - Y + i;
+    const float* src = f >= 0 ? q_rows + static_cast<size_t>(f) * n : h->history.data() + static_cast<size_t>(T + i) * n;
+    std::memcpy(next.data() + static_cast<size_t>(i) * n, src, sizeof(float) * n);
+  }
+  h->history.swap(next);
+  h->box = h->q = nullptr;
+  return 0;
+}
+
 // append the object representation of a field (the reference writes through reinterpret_cast on a little-endian host)
 static void put_bytes(uint8_t* out, size_t& at, const void* v, size_t n) {
   std::memcpy(out + at, v, n);
