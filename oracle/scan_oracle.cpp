@@ -490,14 +490,19 @@ struct orc_chain {
     }
   }
 
-  int push(const void* iq, size_t nFrames, int64_t t0, double period, const orc_outputs* out) {
+  // psdRows != nullptr: the frames' PSD rows are given (everything after PSD::work); otherwise they are computed from iq
+  int push(const void* iq, const float* psdRows, size_t nFrames, int64_t t0, double period, const orc_outputs* out) {
     const int n = cfg.fft_size;
     const size_t bytesPerSample = cfg.iq_format == 0 ? 2 : 8;
     for (size_t k = 0; k < nFrames; ++k) {
       const int64_t now = t0 + static_cast<int64_t>(std::floor(static_cast<double>(k) * period + 0.5));
-      // stream_to_vector + Decimator: first N samples of each r*N group (decimator.h:16-22)
-      const char* frame = static_cast<const char*>(iq) + k * static_cast<size_t>(cfg.frame_stride_samples) * bytesPerSample;
-      framePsd(frame, psd.data(), nullptr);
+      if (psdRows) {
+        std::memcpy(psd.data(), psdRows + k * n, sizeof(float) * n);
+      } else {
+        // stream_to_vector + Decimator: first N samples of each r*N group (decimator.h:16-22)
+        const char* frame = static_cast<const char*>(iq) + k * static_cast<size_t>(cfg.frame_stride_samples) * bytesPerSample;
+        framePsd(frame, psd.data(), nullptr);
+      }
       if (out && out->psd_db) std::memcpy(out->psd_db + k * n, psd.data(), sizeof(float) * n);
       spectrogram(psd.data(), now);  // wired to the raw PSD, sdr_device.cpp:170-171
 
@@ -529,7 +534,10 @@ orc_chain* orc_chain_create(const orc_config* cfg) {
   return new orc_chain(*cfg);
 }
 void orc_chain_destroy(orc_chain* c) { delete c; }
-int orc_chain_push(orc_chain* c, const void* iq, size_t n, int64_t t0, double period, const orc_outputs* out) { return c->push(iq, n, t0, period, out); }
+int orc_chain_push(orc_chain* c, const void* iq, size_t n, int64_t t0, double period, const orc_outputs* out) { return c->push(iq, nullptr, n, t0, period, out); }
+int orc_chain_push_psd(orc_chain* c, const float* psd_rows, size_t n, int64_t t0, double period, const orc_outputs* out) {
+  return psd_rows ? c->push(nullptr, psd_rows, n, t0, period, out) : -1;
+}
 void orc_chain_reset(orc_chain* c) {
   c->signals.clear();
   c->averager.reset();
@@ -692,7 +700,7 @@ double orc_bench_run(const orc_config* cfg, const void* iq, size_t nFrames, doub
       out.tx_count = cnt.data();
       out.tx_freq = freq.data();
       out.tx_flush = fl.data();
-      chains[t]->push(base, count, 0, period, &out);
+      chains[t]->push(base, nullptr, count, 0, period, &out);
     });
   }
   for (auto& th : pool) th.join();

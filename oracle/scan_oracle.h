@@ -81,6 +81,8 @@ orc_chain* orc_chain_create(const orc_config* cfg);
 void orc_chain_destroy(orc_chain* c);
 /* frame k is stamped now_k = t0_ms + floor(k*frame_period_ms + 0.5) */
 int orc_chain_push(orc_chain* c, const void* iq, size_t n_frames, int64_t t0_ms, double frame_period_ms, const orc_outputs* out);
+/* same from the PSD rows on (psd_rows[n_frames][N] = what PSD::work emitted): noiseLearner -> transmission, psd -> spectrogram */
+int orc_chain_push_psd(orc_chain* c, const float* psd_rows, size_t n_frames, int64_t t0_ms, double frame_period_ms, const orc_outputs* out);
 void orc_chain_reset(orc_chain* c);                                    /* Transmission::resetBuffers, transmission.cpp:42-55 */
 void orc_chain_set_center(orc_chain* c, int32_t center, int32_t lo, int32_t hi); /* sdr_device.cpp:77 */
 void orc_chain_get_averager(orc_chain* c, float* sum, float* avg, float* ring, int32_t* frames);

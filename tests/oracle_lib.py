@@ -48,6 +48,7 @@ def oracle():
         L.orc_chain_create.argtypes = [C.POINTER(BandConfig)]
         L.orc_chain_destroy.argtypes = [C.c_void_p]
         L.orc_chain_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_double, C.POINTER(Outputs)]
+        L.orc_chain_push_psd.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_double, C.POINTER(Outputs)]
         L.orc_chain_reset.argtypes = [C.c_void_p]
         L.orc_chain_set_center.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.orc_chain_get_averager.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
@@ -240,7 +241,8 @@ class OracleChain:
         self.h = C.c_void_p(self.L.orc_chain_create(C.byref(self.cfg)))
         assert self.h, "orc_chain_create failed"
 
-    def push(self, iq, n_frames, t0_ms, period_ms, dense=("psd_db", "noise_sub_db", "avg_db", "box_db")):
+    def push(self, iq, n_frames, t0_ms, period_ms, dense=("psd_db", "noise_sub_db", "avg_db", "box_db"), psd_rows=False):
+        """iq: the frames' IQ samples — or, with psd_rows=True, their PSD rows [n_frames][N] (the chain from PSD::work's output on)."""
         n = self.cfg.fft_size
         iq = np.ascontiguousarray(iq)
         r = ChainResult()
@@ -260,7 +262,10 @@ class OracleChain:
         r.tx_power = np.zeros((n_frames, MAX_TX), dtype=np.float32)
         for name in ("peak_index", "tx_count", "tx_freq", "tx_flush", "tx_key", "tx_power"):
             setattr(o, name, getattr(r, name).ctypes.data)
-        rc = self.L.orc_chain_push(self.h, _p(iq), n_frames, t0_ms, period_ms, C.byref(o))
+        if psd_rows:
+            rc = self.L.orc_chain_push_psd(self.h, _p(np.ascontiguousarray(iq, dtype=np.float32)), n_frames, t0_ms, period_ms, C.byref(o))
+        else:
+            rc = self.L.orc_chain_push(self.h, _p(iq), n_frames, t0_ms, period_ms, C.byref(o))
         assert rc == 0
         r.frame_tx = [
             [(int(r.tx_freq[k, s]), int(r.tx_flush[k, s]), int(r.tx_key[k, s]), float(r.tx_power[k, s])) for s in range(min(int(r.tx_count[k]), MAX_TX))]
