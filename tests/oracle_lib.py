@@ -147,10 +147,11 @@ class RefBlocksChain:
         n = self.cfg.fft_size
         row = np.ascontiguousarray(psd_row, dtype=np.float32)
         q = np.empty(n, dtype=np.float32)
-        freq = np.zeros(MAX_TX, dtype=np.int32)
-        flush = np.zeros(MAX_TX, dtype=np.int32)
-        k = self.L.ref_chain_push_row(self.h, _p(row), int(now_ms), _p(q), _p(freq), _p(flush), MAX_TX)
-        return q, [(int(freq[i]), int(flush[i])) for i in range(min(k, MAX_TX))]
+        cap = 1024  # the reference's list is unbounded; the oracle / engine report the first MAX_TX entries
+        freq = np.zeros(cap, dtype=np.int32)
+        flush = np.zeros(cap, dtype=np.int32)
+        k = self.L.ref_chain_push_row(self.h, _p(row), int(now_ms), _p(q), _p(freq), _p(flush), cap)
+        return q, [(int(freq[i]), int(flush[i])) for i in range(min(k, cap))]
 
     def reset(self):
         self.L.ref_chain_reset(self.h)
