@@ -36,11 +36,14 @@ extern "C" {
 #define B2S_E_INVALID (-1)   /* bad argument / unsupported configuration */
 #define B2S_E_CUDA (-2)      /* CUDA runtime error (sticky errors: destroy and re-create the engine) */
 #define B2S_E_NOMEM (-3)
-#define B2S_E_OVERFLOW (-4)  /* detection list capacity exceeded; raise detect_capacity */
+#define B2S_E_OVERFLOW (-4)  /* a frame had more detection entries than detect_capacity: the push completed on truncated lists (state
+                                stays consistent), the capacity grows before the next push; or more live signals than the engine tracks */
 #define B2S_E_STATE (-5)
 
 #define B2S_MAX_IGNORED 16
-#define B2S_MAX_TX 64        /* max simultaneously tracked transmissions per band */
+#define B2S_MAX_TX 64        /* transmissions held INSIDE b2s_result; the signal map itself is not limited to this (the reference's
+                                std::map is unbounded): n_transmissions_total reports the real count and
+                                b2s_band_get_transmissions returns the whole list */
 
 #define B2S_IQ_CS8 0         /* interleaved int8 I,Q (help_structures.h:17 SimpleComplex) */
 #define B2S_IQ_CF32 1        /* interleaved float I,Q (what SdrSource delivers, sdr_source.cpp:52) */
@@ -58,7 +61,8 @@ extern "C" {
 /* Construction-time parameters. The reference takes them from Config / Device / the setupChains lambdas
  * (sdr_device.cpp:148-167, transmission.h:17-25, config.h:24-38). */
 typedef struct b2s_band_config {
-  int32_t fft_size;             /* N = getFft(fs, SIGNAL_DETECTION_MAX_STEP); power of two, 256..32768 */
+  int32_t fft_size;             /* N = getFft(fs, SIGNAL_DETECTION_MAX_STEP); power of two, 256..262144 (sizes above 16384 run as 16384-point
+                                   residue classes of the bin index, see csrc/spectral3.cuh) */
   int32_t sample_rate_hz;       /* Device::m_sampleRate (Frequency = int32_t) */
   int32_t frame_stride_samples; /* fftSize * decimatorFactor complex samples between frame starts (sdr_device.cpp:161-163) */
   int32_t iq_format;            /* B2S_IQ_* */
@@ -86,7 +90,7 @@ typedef struct b2s_band_config {
   int32_t flags;                /* B2S_FLAG_* */
   /* ---- engine-only sizing (ignored by the oracle) ---- */
   int32_t max_frames_per_push;  /* capacity of the per-push device buffers; 0 -> 4096 */
-  int32_t detect_capacity;      /* detection entries kept per FRAME (bins >= min(start,stop)); 0 -> 256 */
+  int32_t detect_capacity;      /* detection entries kept per FRAME (bins >= min(start,stop)); 0 -> clamp(N/8, 256, 4096); grows on overflow */
 } b2s_band_config;
 
 /* Fill cfg with the reference's defaults for a device with this sample rate, exactly as setupChains sizes the chain
@@ -119,6 +123,8 @@ typedef struct b2s_result {
   /* statistics */
   int32_t n_detect_entries;         /* bins >= min(start,stop) level found in this push */
   int32_t n_spectrogram_rows;       /* rows completed during this push (fetch with b2s_band_get_spectrogram) */
+  int32_t n_transmissions_total;    /* live transmissions after the last frame; when > B2S_MAX_TX, transmissions[] holds the
+                                       B2S_MAX_TX strongest and b2s_band_get_transmissions the complete list */
 } b2s_result;
 
 typedef struct b2s_engine b2s_engine;
@@ -167,8 +173,12 @@ int b2s_band_set_center(b2s_band* b, int32_t center_hz, int32_t range_lo_hz, int
 /* ---- state introspection (reference: Averager::average()/data(), averager.h:15-16) ---- */
 int b2s_band_get_averager(b2s_band* b, float* sum /*[N]*/, float* avg /*[N]*/, float* ring /*[Y][N] oldest->newest*/, int32_t* frames);
 int b2s_band_get_noise(b2s_band* b, float* threshold /*[N]*/, int32_t* samples, int32_t* ready);
-/* completed spectrogram rows (Spectrogram::send, spectrogram.cpp:62-75) since the last call with consume != 0 */
+/* completed spectrogram rows (Spectrogram::send, spectrogram.cpp:62-75), oldest first: up to `cap` rows are copied, *count is
+ * the number available; with consume != 0 the rows copied out (and only those) are dropped from the band's list */
 int b2s_band_get_spectrogram(b2s_band* b, int64_t* times_ms, int32_t* centers_hz, int8_t* rows /*[cap][out_size]*/, int cap, int consume, int* count);
+/* the complete mailbox after the last finished push (Transmission::getSortedTransmissions, transmission.cpp:166-176), strongest
+ * first; up to `cap` entries are copied, *count is the number of live transmissions */
+int b2s_band_get_transmissions(b2s_band* b, b2s_transmission* out, int cap, int* count);
 /* live signals (the std::map<Index, Signal> of transmission.h:49) */
 int b2s_band_get_signals(b2s_band* b, int32_t* keys, int64_t* first_ms, int64_t* last_ms, float* power, int cap, int* count);
 
@@ -189,6 +199,10 @@ int b2s_averager_sum(b2s_averager* a, float* out, int32_t* frames);       /* m_s
 int b2s_average(b2s_engine* e, const float* in, float* out, int size, int group_size, int rows, int exact);
 /* IQ -> raw PSD rows (unpack, window, FFT, shift, dB) only; power_lin optional (|X|^2/fs) */
 int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_frames, float* psd_db, float* power_lin);
+
+/* Self-test: the 3-instruction exact division by a small constant that the Averager (m_sum / GROUPING_Y, averager.cpp:52-60) and
+ * boxcar fast paths use, compared with IEEE division for EVERY float with |x| in [2^-60, 2^61) and +-0. *mismatches must be 0. */
+int b2s_selftest_div_const(b2s_engine* e, int divisor, uint64_t* mismatches);
 
 /* ---- host helpers with the reference's semantics (used by the tracker; exported for the adaptor and for tests) ---- */
 int b2s_get_fft(int32_t sample_rate_hz, int32_t max_step_hz);                                  /* radio_utils.cpp:98-104 */

@@ -407,8 +407,10 @@ struct orc_chain {
   }
 
   // sources/radio/blocks/transmission.cpp:57-68, with `now` injected
+  int64_t lastNow = 0;  // clock of the most recent frame (for orc_chain_get_transmissions)
   void detect(const float* power, int64_t now, int frameNo, const orc_outputs* out) {
     const int n = cfg.fft_size;
+    lastNow = now;
     averager.push(power);
     boxcar(averager.mean.data(), box.data(), n, cfg.grouping_x);
     if (out && out->avg_db) std::memcpy(out->avg_db + static_cast<size_t>(frameNo) * n, averager.mean.data(), sizeof(float) * n);
@@ -581,6 +583,36 @@ int orc_chain_get_spectrogram(orc_chain* c, int64_t* times, int32_t* centers, in
   return count;
 }
 void orc_chain_clear_spectrogram(orc_chain* c) { c->sent.clear(); }
+
+// the live std::map<Index, Signal> (transmission.h:49) in key order
+int orc_chain_get_signals(orc_chain* c, int32_t* keys, int64_t* first, int64_t* last, float* power, int cap) {
+  int i = 0;
+  for (const auto& kv : c->signals) {
+    if (i < cap) {
+      if (keys) keys[i] = kv.first;
+      if (first) first[i] = kv.second.first;
+      if (last) last[i] = kv.second.last;
+      if (power) power[i] = kv.second.power;
+    }
+    ++i;
+  }
+  return i;
+}
+// getSortedTransmissions (transmission.cpp:166-176) after the most recent frame, without the ORC_MAX_TX bound of orc_outputs
+int orc_chain_get_transmissions(orc_chain* c, int32_t* freq, int32_t* flush, int32_t* key, float* power, int cap) {
+  std::vector<int> keys;
+  for (const auto& kv : c->signals) keys.push_back(kv.first);
+  std::stable_sort(keys.begin(), keys.end(), [&](int a, int b) { return c->signals.at(a).power > c->signals.at(b).power; });
+  const int64_t now = c->lastNow;
+  for (int s = 0; s < static_cast<int>(keys.size()) && s < cap; ++s) {
+    const auto& sig = c->signals.at(keys[s]);
+    if (freq) freq[s] = tuned(c->indexToShift(keys[s]), c->cfg.tuning_step_hz);
+    if (flush) flush[s] = ((sig.last == now) && (sig.first + c->cfg.min_time_ms <= now)) ? 1 : 0;
+    if (key) key[s] = keys[s];
+    if (power) power[s] = sig.power;
+  }
+  return static_cast<int>(keys.size());
+}
 
 void orc_hamming(int n, float* w) { hamming(n, w); }
 void orc_fft_f64(int n, const float* in, float* out) {

@@ -90,6 +90,10 @@ int orc_chain_get_noise(orc_chain* c, float* thr, int32_t* samples);  /* returns
 /* spectrogram rows sent so far (spectrogram.cpp:62-75): returns count; copies up to cap rows */
 int orc_chain_get_spectrogram(orc_chain* c, int64_t* times, int32_t* centers, int8_t* rows, int cap);
 void orc_chain_clear_spectrogram(orc_chain* c);
+/* live signals in key order (the std::map of transmission.h:49); returns the count, copies up to cap */
+int orc_chain_get_signals(orc_chain* c, int32_t* keys, int64_t* first_ms, int64_t* last_ms, float* power, int cap);
+/* the complete getSortedTransmissions list after the most recent frame (not bounded by ORC_MAX_TX); returns the count */
+int orc_chain_get_transmissions(orc_chain* c, int32_t* freq, int32_t* flush, int32_t* key, float* power, int cap);
 
 /* stand-alone operators */
 void orc_hamming(int n, float* w);

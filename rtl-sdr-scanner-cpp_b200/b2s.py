@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2s.so")
+LIB_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "lib", "libb2s.so")  # B2S_LIB: an A/B build of the same ABI (measurements)
 
 MAX_IGNORED = 16
 MAX_TX = 64
@@ -76,6 +76,7 @@ class Result(C.Structure):
         ("box_db", C.POINTER(C.c_float)),
         ("n_detect_entries", C.c_int32),
         ("n_spectrogram_rows", C.c_int32),
+        ("n_transmissions_total", C.c_int32),
     ]
 
 
@@ -190,6 +191,7 @@ def lib():
         L.b2s_band_get_averager.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.b2s_band_get_noise.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.b2s_band_get_spectrogram.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.b2s_band_get_transmissions.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.b2s_band_get_signals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.b2s_averager_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.b2s_averager_destroy.argtypes = [C.c_void_p]
@@ -250,6 +252,13 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def check_div_const(self, divisor: int) -> int:
+        """Mismatches of the engine's exact constant division against IEEE division over its whole guarded range (must be 0)."""
+        bad = C.c_uint64()
+        lib().b2s_selftest_div_const.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        _check(lib().b2s_selftest_div_const(self._h, divisor, C.byref(bad)))
+        return bad.value
 
     # ---- stand-alone operators ----
     def average(self, data: np.ndarray, group_size: int, exact: bool = False) -> np.ndarray:
@@ -432,6 +441,13 @@ class Band:
         _check(lib().b2s_band_get_spectrogram(self._h, _ptr(times), _ptr(centers), _ptr(rows), cap, 1 if consume else 0, C.byref(count)))
         k = min(count.value, cap)
         return times[:k], centers[:k], rows[:k]
+
+    def get_transmissions(self, cap: int = 4096):
+        """The complete mailbox after the last finished push, strongest first: [(shift_hz, flush, key, power)]."""
+        tx = (Transmission * cap)()
+        count = C.c_int()
+        _check(lib().b2s_band_get_transmissions(self._h, C.cast(tx, C.c_void_p), cap, C.byref(count)))
+        return [(tx[i].shift_hz, tx[i].flush, tx[i].key, tx[i].power) for i in range(min(count.value, cap))]
 
     def get_signals(self, cap: int = MAX_TX):
         keys = np.zeros(cap, dtype=np.int32)

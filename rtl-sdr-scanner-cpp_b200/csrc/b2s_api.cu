@@ -13,13 +13,13 @@
 #include <limits>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/b2s.h"
 #include "detect.cuh"
 #include "host_utils.h"
-#include "spectral2.cuh"
 #include "spectral3.cuh"
 #include "tracker.h"
 
@@ -108,82 +108,84 @@ struct b2s_engine {
   int device = 0;
   cudaDeviceProp prop{};
   int sm_count = 0;
+  // kernels whose function attributes have been set on THIS device -> resident CTAs per SM. Function attributes are per
+  // device, so the cache lives in the engine (one engine per GPU; several engines may share a process).
+  std::mutex attr_mutex;
+  std::map<const void*, int> kernel_ctas;
 };
 
-// K1 launcher -------------------------------------------------------------------------------------------------
 namespace {
 
+// Opt the kernel into `smem` bytes of dynamic shared memory on the engine's device (once per engine) and report how many
+// CTAs of `threads` threads fit on an SM.
+template <typename K>
+int prepare_kernel(b2s_engine* e, K kernel, int threads, size_t smem, int* ctas_per_sm) {
+  std::lock_guard<std::mutex> lk(e->attr_mutex);
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = e->kernel_ctas.find(key);
+  if (it == e->kernel_ctas.end()) {
+    int ctas = 0;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, threads, smem));
+    if (ctas < 1) return fail(B2S_E_CUDA, "a kernel needing %zu bytes of shared memory and %d threads does not fit on an SM of this device", smem, threads);
+    it = e->kernel_ctas.emplace(key, ctas).first;
+  }
+  if (ctas_per_sm) *ctas_per_sm = it->second;
+  return 0;
+}
+
+// K1 launcher -------------------------------------------------------------------------------------------------
 template <int N, int MODE, bool LIN>
-int launch_spectrum_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+int launch_spectrum_v(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   using PL = FftPlanT<N>;
   constexpr int T = N / PL::E;
   const size_t smem = sizeof(float2) * (exchange_elems<N>() + TwiddleLayout<N>::SMEM) + (MODE == kModeCs8Tma ? 2 * N : 0);
-  static bool configured = false;
-  static int ctas_per_sm = 1;
-  if (!configured) {
-    CU(cudaFuncSetAttribute(k_spectrum<N, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum<N, MODE, LIN>, T, smem));
-    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum<%d> does not fit on an SM", N);
-    configured = true;
-  }
+  int ctas_per_sm = 1;
+  int rc = prepare_kernel(e, k_spectrum<N, MODE, LIN>, T, smem, &ctas_per_sm);
+  if (rc) return rc;
   const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
   k_spectrum<N, MODE, LIN><<<grid, T, smem, stream>>>(a);
   CU(cudaGetLastError());
   return 0;
 }
-template <int N, int MODE, bool LIN>
-int launch_spectrum2_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
-  using PL = FftPlanT<N>;
-  constexpr int T = N / PL::E;
-  const size_t smem = sizeof(float) * (2 * plane_elems<N>() + TwiddleLayout2<N>::SMEM) + (MODE == kModeCs8Tma ? 2 * N : 0);
-  static bool configured = false;
-  static int ctas_per_sm = 1;
-  if (!configured) {
-    CU(cudaFuncSetAttribute(k_spectrum2<N, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum2<N, MODE, LIN>, T, smem));
-    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum2<%d> does not fit on an SM", N);
-    configured = true;
+// k_spectrum3: N = RA * 1024 directly (RA = 4, 8, 16), or N = S * 16384 through the split mode (S = a.split > 1)
+template <int RA, int MODE, bool LIN, bool SPLIT>
+int launch_spectrum3_v(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
+  constexpr int T = RA * 32;
+  const size_t smem = sizeof(float2) * (RA * kBlockPitch + 31 * 32) + (MODE == kModeCs8Tma ? (SPLIT ? 2 * kSplitStageBytes : 2 * RA * 1024) : 0);
+  int ctas_per_sm = 1;
+  int rc = prepare_kernel(e, k_spectrum3<RA, MODE, LIN, SPLIT>, T, smem, &ctas_per_sm);
+  if (rc) return rc;
+  if (!a.work_counter) return fail(B2S_E_INVALID, "k_spectrum3 needs a work counter");
+  const int items = a.n_frames * (SPLIT ? a.split : 1);
+  const int grid = std::min(items, e->sm_count * ctas_per_sm);
+  if (SPLIT) {
+    if (!a.peak_packed || !a.split_tw || !a.split_ws) return fail(B2S_E_INVALID, "split-mode tables are missing");
+    CU(cudaMemsetAsync(a.peak_packed, 0, sizeof(unsigned long long) * a.n_frames, stream));
   }
-  const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
-  k_spectrum2<N, MODE, LIN><<<grid, T, smem, stream>>>(a);
+  k_spectrum3<RA, MODE, LIN, SPLIT><<<grid, T, smem, stream>>>(a);
   CU(cudaGetLastError());
-  return 0;
-}
-template <int N, int MODE, bool LIN>
-int launch_spectrum3_v(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
-  constexpr int RA = N / 1024, T = RA * 32;
-  const size_t smem = sizeof(float2) * (RA * kBlockPitch + 31 * 32) + (MODE == kModeCs8Tma ? 2 * N : 0);
-  static bool configured = false;
-  static int ctas_per_sm = 1;
-  if (!configured) {
-    CU(cudaFuncSetAttribute(k_spectrum3<RA, MODE, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spectrum3<RA, MODE, LIN>, T, smem));
-    if (ctas_per_sm < 1) return fail(B2S_E_CUDA, "k_spectrum3<%d> does not fit on an SM", N);
-    configured = true;
+  if (SPLIT) {
+    k_peak_unpack<<<(a.n_frames + 255) / 256, 256, 0, stream>>>(a.peak_packed, a.n_frames, a.peak_index, a.peak_value);
+    CU(cudaGetLastError());
   }
-  const int grid = std::min(a.n_frames, e->sm_count * ctas_per_sm);
-  k_spectrum3<RA, MODE, LIN><<<grid, T, smem, stream>>>(a);
-  CU(cudaGetLastError());
   return 0;
 }
 
-// Which K1 serves which FFT size. 1 = k_spectrum (Stockham, two barriers per pass), 2 = k_spectrum2 (same structure,
-// packed f32x2 arithmetic; measured slower, kept for A/B builds with -DB2S_K1_LARGE=2), 3 = k_spectrum3 (warp-local).
-#ifndef B2S_K1_LARGE
-#define B2S_K1_LARGE 3
-#endif
-constexpr int k1_variant(int n) { return n >= 4096 ? B2S_K1_LARGE : 1; }
+// Which K1 serves which FFT size: k_spectrum (Stockham, two barriers per pass) below 4096, k_spectrum3 (warp-local passes) for
+// 4096 / 8192 / 16384, and k_spectrum3's split mode (S residue classes x 16384 points) for 32768 ... 262144.
+constexpr int kMaxFft = 16 * kSplitM;
+constexpr bool k1_is_v3(int n) { return n >= 4096; }
 
 template <int N, int MODE>
-int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
-  if (!a.peak_index || !a.peak_value) return fail(B2S_E_INVALID, "peak buffers are required");
+int launch_spectrum_t(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   // the |X|^2/fs debug rows come from a debug twin of each instantiation (parity tests); the product one stays lean
-  if constexpr (k1_variant(N) == 3) {
-    if (a.power_lin) return launch_spectrum3_v<N, MODE, true>(e, a, stream);
-    return launch_spectrum3_v<N, MODE, false>(e, a, stream);
-  } else if constexpr (k1_variant(N) == 2) {
-    if (a.power_lin) return launch_spectrum2_v<N, MODE, true>(e, a, stream);
-    return launch_spectrum2_v<N, MODE, false>(e, a, stream);
+  if constexpr (N > kSplitM) {
+    if (a.power_lin) return launch_spectrum3_v<16, MODE, true, true>(e, a, stream);
+    return launch_spectrum3_v<16, MODE, false, true>(e, a, stream);
+  } else if constexpr (k1_is_v3(N)) {
+    if (a.power_lin) return launch_spectrum3_v<N / 1024, MODE, true, false>(e, a, stream);
+    return launch_spectrum3_v<N / 1024, MODE, false, false>(e, a, stream);
   } else {
     if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
     return launch_spectrum_v<N, MODE, false>(e, a, stream);
@@ -191,7 +193,8 @@ int launch_spectrum_t(const b2s_engine* e, const SpectralArgs& a, cudaStream_t s
 }
 
 template <int MODE>
-int launch_spectrum_n(const b2s_engine* e, int n, const SpectralArgs& a, cudaStream_t stream) {
+int launch_spectrum_n(b2s_engine* e, int n, const SpectralArgs& a, cudaStream_t stream) {
+  if (!a.peak_index || !a.peak_value) return fail(B2S_E_INVALID, "peak buffers are required");
   switch (n) {
     case 256: return launch_spectrum_t<256, MODE>(e, a, stream);
     case 512: return launch_spectrum_t<512, MODE>(e, a, stream);
@@ -200,11 +203,14 @@ int launch_spectrum_n(const b2s_engine* e, int n, const SpectralArgs& a, cudaStr
     case 4096: return launch_spectrum_t<4096, MODE>(e, a, stream);
     case 8192: return launch_spectrum_t<8192, MODE>(e, a, stream);
     case 16384: return launch_spectrum_t<16384, MODE>(e, a, stream);
-    default: return fail(B2S_E_INVALID, "fft_size %d is not supported (256..16384)", n);
+    case 32768: case 65536: case 131072: case 262144:
+      if (a.split != n / kSplitM) return fail(B2S_E_INVALID, "split tables were built for another fft_size");
+      return launch_spectrum_t<2 * kSplitM, MODE>(e, a, stream);  // one instantiation serves every S (a.split)
+    default: return fail(B2S_E_INVALID, "fft_size %d is not supported (256..%d)", n, kMaxFft);
   }
 }
 
-int launch_spectrum(const b2s_engine* e, int n, int iq_format, const SpectralArgs& a, cudaStream_t stream) {
+int launch_spectrum(b2s_engine* e, int n, int iq_format, const SpectralArgs& a, cudaStream_t stream) {
   if (iq_format == B2S_IQ_CF32) return launch_spectrum_n<kModeCf32>(e, n, a, stream);
   const bool aligned = (reinterpret_cast<uintptr_t>(a.iq) % 16 == 0) && (a.frame_stride_bytes % 16 == 0);
   if (aligned) return launch_spectrum_n<kModeCs8Tma>(e, n, a, stream);
@@ -226,13 +232,15 @@ void plan_radices(int n, int* r) {
     case 2048: plan_radices_t<2048>(r); break;
     case 4096: plan_radices_t<4096>(r); break;
     case 8192: plan_radices_t<8192>(r); break;
-    default: plan_radices_t<16384>(r); break;
+    default: plan_radices_t<2048>(r); break;  // larger sizes run k_spectrum3, which has its own tables
   }
 }
 
 struct SpectralTables {
   DevBuf<float> wscale;
-  DevBuf<float2> twiddle;
+  DevBuf<float2> twiddle, split_tw, split_ws;
+  DevBuf<int> work_counter;  // k_spectrum3's {next item, finished CTAs}; the kernel leaves both at zero
+  int split = 1;
   int build(const b2s_band_config& cfg) {
     const int n = cfg.fft_size;
     std::vector<float> w;
@@ -241,45 +249,29 @@ struct SpectralTables {
       // unpack scale folded into the window: x*scale*w -> x*(scale*w); differs from the two-step product by < 1 ulp
       for (int i = 0; i < n; ++i) w[i] = w[i] * cfg.iq_scale;
     }
+    split = n > kSplitM ? n / kSplitM : 1;
+    const int m = n / split;  // length of the transform the passes run (the whole FFT, or one residue class of it)
     std::vector<float2> tw;
-    if (k1_variant(n) == 3) {
-      // k_spectrum3 (TwiddleLayout3): pass A  W_N^(b*k0) as [k0-1][b], b < 1024;  pass B  W_1024^(n2*k1) as [k1-1][n2]
-      const int ra = n / 1024;
+    auto root = [](double num, double den) {
+      const double ang = -2.0 * M_PI * num / den;
+      return make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+    };
+    if (k1_is_v3(m)) {
+      // k_spectrum3 (TwiddleLayout3): pass A  W_m^(b*k0) as [k0-1][b], b < 1024;  pass B  W_1024^(n2*k1) as [k1-1][n2]
+      const int ra = m / 1024;
       for (int k0 = 1; k0 < ra; ++k0)
-        for (int b = 0; b < 1024; ++b) {
-          const double ang = -2.0 * M_PI * (static_cast<double>(b) * k0) / n;
-          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
-        }
+        for (int b = 0; b < 1024; ++b) tw.push_back(root(static_cast<double>(b) * k0, m));
       for (int k1 = 1; k1 < 32; ++k1)
-        for (int n2 = 0; n2 < 32; ++n2) {
-          const double ang = -2.0 * M_PI * (static_cast<double>(n2) * k1) / 1024.0;
-          tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
-        }
+        for (int n2 = 0; n2 < 32; ++n2) tw.push_back(root(static_cast<double>(n2) * k1, 1024.0));
     } else {
-      // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)): interleaved (re, im) in the order of TwiddleLayout<N>
-      // for k_spectrum; planar (real plane, then imaginary plane, per pass) in the order of TwiddleLayout2<N> for k_spectrum2
+      // per-pass compact tables [m-1][k] = exp(-2 pi i k m / (P R)), interleaved (re, im), in the order of TwiddleLayout<N>
       int radix[4] = {0, 0, 0, 0};
       plan_radices(n, radix);
       int P = radix[0];
-      const bool planar = k1_variant(n) == 2;
       for (int pass = 1; pass < 4 && radix[pass] > 1; ++pass) {
         const int R = radix[pass];
-        std::vector<float> pr, pi;
-        for (int m = 1; m < R; ++m) {
-          for (int k = 0; k < P; ++k) {
-            const double ang = -2.0 * M_PI * (static_cast<double>(k) * m) / (static_cast<double>(P) * R);
-            if (planar) {
-              pr.push_back(static_cast<float>(std::cos(ang)));
-              pi.push_back(static_cast<float>(std::sin(ang)));
-            } else {
-              tw.push_back(make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang))));
-            }
-          }
-        }
-        if (planar) {  // (R-1)*P is even, so the planes pack into float2 slots exactly
-          for (size_t i = 0; i + 1 < pr.size(); i += 2) tw.push_back(make_float2(pr[i], pr[i + 1]));
-          for (size_t i = 0; i + 1 < pi.size(); i += 2) tw.push_back(make_float2(pi[i], pi[i + 1]));
-        }
+        for (int mm = 1; mm < R; ++mm)
+          for (int k = 0; k < P; ++k) tw.push_back(root(static_cast<double>(k) * mm, static_cast<double>(P) * R));
         P *= R;
       }
     }
@@ -289,16 +281,41 @@ struct SpectralTables {
     if (rc) return rc;
     CU(cudaMemcpy(wscale.p, w.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(twiddle.p, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+    if ((rc = work_counter.alloc(2))) return rc;
+    CU(cudaMemset(work_counter.p, 0, sizeof(int) * 2));
+    if (split > 1) {
+      // split mode: class twiddles W_N^(n' c) as [c][n'] (n' c < N^2 fits a double exactly), and the S-th roots of unity
+      std::vector<float2> tc(static_cast<size_t>(split) * m), ws(split);
+      for (int c = 0; c < split; ++c)
+        for (int i = 0; i < m; ++i) tc[static_cast<size_t>(c) * m + i] = root(std::fmod(static_cast<double>(i) * c, static_cast<double>(n)), n);
+      for (int j = 0; j < split; ++j) ws[j] = root(j, split);
+      if ((rc = split_tw.alloc(tc.size()))) return rc;
+      if ((rc = split_ws.alloc(ws.size()))) return rc;
+      CU(cudaMemcpy(split_tw.p, tc.data(), sizeof(float2) * tc.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(split_ws.p, ws.data(), sizeof(float2) * ws.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
+  }
+  // the table pointers of a K1 launch
+  void fill(SpectralArgs& sa) const {
+    sa.wscale = wscale.p;
+    sa.twiddle = twiddle.p;
+    sa.work_counter = work_counter.p;
+    sa.split = split;
+    sa.split_tw = split_tw.p;
+    sa.split_ws = split_ws.p;
   }
   void release() {
     wscale.release();
     twiddle.release();
+    split_tw.release();
+    split_ws.release();
+    work_counter.release();
   }
 };
 
 int validate_config(const b2s_band_config& c) {
-  if (!is_pow2(c.fft_size) || c.fft_size < 256 || c.fft_size > 16384) return fail(B2S_E_INVALID, "fft_size must be a power of two in 256..16384 (got %d)", c.fft_size);
+  if (!is_pow2(c.fft_size) || c.fft_size < 256 || c.fft_size > kMaxFft) return fail(B2S_E_INVALID, "fft_size must be a power of two in 256..%d (got %d)", kMaxFft, c.fft_size);
   if (c.sample_rate_hz <= 0) return fail(B2S_E_INVALID, "sample_rate_hz must be positive");
   if (c.frame_stride_samples < c.fft_size) return fail(B2S_E_INVALID, "frame_stride_samples (%d) < fft_size", c.frame_stride_samples);
   if (c.iq_format != B2S_IQ_CS8 && c.iq_format != B2S_IQ_CF32) return fail(B2S_E_INVALID, "unknown iq_format %d", c.iq_format);
@@ -370,6 +387,14 @@ struct b2s_averager {
     return 0;
   }
 };
+
+// ---- self-test of the exact constant division used on the Averager / boxcar fast paths (detect.cuh: div_const) ----
+template <int D>
+static int run_div_check(unsigned long long* d_bad) {
+  k_check_div_const<D><<<148 * 8, 256>>>(d_bad);
+  CU(cudaGetLastError());
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // C-ABI
@@ -474,10 +499,15 @@ int b2s_band_push(b2s_band* b, const void* iq, size_t n_frames, int64_t t0_ms, d
   if (b->async_mode && out) return fail(B2S_E_INVALID, "with B2S_FLAG_ASYNC results are collected by b2s_band_sync; pass out = NULL to b2s_band_push");
   if (out) {
     out->n_transmissions = 0;
+    out->n_transmissions_total = 0;
     out->n_detect_entries = 0;
     out->n_spectrogram_rows = 0;
   }
   b->prof.pushes += 1;
+  {
+    int rc = b->grow_capacity();  // a previous push overflowed its per-frame entry lists
+    if (rc) return rc;
+  }
   const size_t bytes_per_sample = b->cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
   const size_t stride_bytes = static_cast<size_t>(b->cfg.frame_stride_samples) * bytes_per_sample;
   const bool on_device = (b->cfg.flags & B2S_FLAG_IQ_ON_DEVICE) != 0;
@@ -560,8 +590,9 @@ int b2s_band_sync(b2s_band* b, b2s_result* out) {
   int rc = b->drain();
   if (rc) return rc;
   if (out) {
-    out->n_transmissions = b->mailbox_count;
-    std::memcpy(out->transmissions, b->mailbox, sizeof(b2s_transmission) * b->mailbox_count);
+    out->n_transmissions_total = static_cast<int32_t>(b->mailbox.size());
+    out->n_transmissions = std::min<int32_t>(out->n_transmissions_total, B2S_MAX_TX);
+    std::memcpy(out->transmissions, b->mailbox.data(), sizeof(b2s_transmission) * out->n_transmissions);
     out->n_detect_entries = b->stat_entries;
     out->n_spectrogram_rows = b->stat_rows;
   }
@@ -667,7 +698,18 @@ int b2s_band_get_spectrogram(b2s_band* b, int64_t* times, int32_t* centers, int8
     if (rows) std::memcpy(rows + static_cast<size_t>(i) * M, b->sent[i].row.data(), M);
   }
   *count = total;
-  if (consume) b->sent.clear();
+  if (consume) b->sent.erase(b->sent.begin(), b->sent.begin() + std::min(total, std::max(cap, 0)));  // only the rows handed out
+  return 0;
+}
+
+int b2s_band_get_transmissions(b2s_band* b, b2s_transmission* out, int cap, int* count) {
+  if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(b->mutex);
+  int rc = b->drain();
+  if (rc) return rc;
+  const int total = static_cast<int>(b->mailbox.size());
+  if (out) std::memcpy(out, b->mailbox.data(), sizeof(b2s_transmission) * std::max(0, std::min(cap, total)));
+  *count = total;
   return 0;
 }
 
@@ -793,6 +835,7 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   DevBuf<unsigned char> diq;
   DevBuf<float> dpsd, dlin, dpv;
   DevBuf<int> dpi;
+  DevBuf<unsigned long long> dpacked;
   const size_t n = c.fft_size;
   const size_t bps = c.iq_format == B2S_IQ_CS8 ? 2 : 8;
   const size_t stride = static_cast<size_t>(c.frame_stride_samples) * bps;
@@ -803,6 +846,7 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   if (!rc && power_lin) rc = dlin.alloc(n_frames * n);
   if (!rc) rc = dpv.alloc(n_frames);
   if (!rc) rc = dpi.alloc(n_frames);
+  if (!rc && tables.split > 1) rc = dpacked.alloc(n_frames);
   cudaError_t err = cudaSuccess;
   if (!rc) err = cudaMemcpy(diq.p, iq, bytes, cudaMemcpyHostToDevice);
   if (!rc && err == cudaSuccess) {
@@ -810,13 +854,13 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
     sa.iq = diq.p;
     sa.frame_stride_bytes = static_cast<long long>(stride);
     sa.n_frames = static_cast<int>(n_frames);
-    sa.wscale = tables.wscale.p;
-    sa.twiddle = tables.twiddle.p;
+    tables.fill(sa);
     sa.inv_fs = 1.0f / static_cast<float>(c.sample_rate_hz);
     sa.psd_db = dpsd.p;
     sa.power_lin = power_lin ? dlin.p : nullptr;
     sa.peak_index = dpi.p;
     sa.peak_value = dpv.p;
+    sa.peak_packed = dpacked.p;
     rc = launch_spectrum(e, c.fft_size, c.iq_format, sa, nullptr);
     if (!rc) err = cudaDeviceSynchronize();
     if (!rc && err == cudaSuccess) err = cudaMemcpy(psd_db, dpsd.p, sizeof(float) * n_frames * n, cudaMemcpyDeviceToHost);
@@ -828,8 +872,41 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   dlin.release();
   dpv.release();
   dpi.release();
+  dpacked.release();
   if (rc) return rc;
   if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_psd: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+// self-test of the exact constant division (k_check_div_const above)
+int b2s_selftest_div_const(b2s_engine* e, int divisor, uint64_t* mismatches) {
+  if (!e || !mismatches) return fail(B2S_E_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  DevBuf<unsigned long long> bad;
+  int rc = bad.alloc(1);
+  if (rc) return rc;
+  cudaMemset(bad.p, 0, sizeof(unsigned long long));
+  switch (divisor) {
+    case 2: rc = run_div_check<2>(bad.p); break;
+    case 3: rc = run_div_check<3>(bad.p); break;
+    case 5: rc = run_div_check<5>(bad.p); break;
+    case 7: rc = run_div_check<7>(bad.p); break;
+    case 9: rc = run_div_check<9>(bad.p); break;
+    case 11: rc = run_div_check<11>(bad.p); break;
+    case 13: rc = run_div_check<13>(bad.p); break;
+    case 15: rc = run_div_check<15>(bad.p); break;
+    case 17: rc = run_div_check<17>(bad.p); break;
+    case 19: rc = run_div_check<19>(bad.p); break;
+    case 21: rc = run_div_check<21>(bad.p); break;
+    default: rc = fail(B2S_E_INVALID, "no div_const instantiation for divisor %d", divisor);
+  }
+  unsigned long long h = 0;
+  cudaError_t err = cudaSuccess;
+  if (!rc) err = cudaMemcpy(&h, bad.p, sizeof(h), cudaMemcpyDeviceToHost);
+  bad.release();
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_selftest_div_const: %s", cudaGetErrorString(err));
+  *mismatches = h;
   return 0;
 }
 

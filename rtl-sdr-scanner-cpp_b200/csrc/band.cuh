@@ -41,7 +41,7 @@ struct PushSlot {
   DevBuf<DetectEntry> sorted;
   DevBuf<signed char> spec_rows;
   DevBuf<unsigned int> watch_max;
-  DevBuf<unsigned long long> cta_ns;
+  DevBuf<unsigned long long> cta_ns, peak_packed;
   CUtensorMap psd_map;  // PSD rows [max_frames][N] as a 2-D tensor, box = [32 frames][128 + 2*halo columns] (K2's tile)
   DevBuf<int> cand_flag;
   PinBuf<int> h_offsets, h_cand_flag;
@@ -68,7 +68,7 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
-    h_offsets.release(); h_entries.release(); watch_max.release(); cta_ns.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
+    h_offsets.release(); h_entries.release(); watch_max.release(); cta_ns.release(); peak_packed.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
     if (gpu_done) cudaEventDestroy(gpu_done);
     for (auto& e : ev) {
       if (e) cudaEventDestroy(e);
@@ -85,6 +85,8 @@ struct b2s_band : public DeviceQueries {
   int iq_slot = 0;
   int max_frames = 0;
   int slot_capacity = 0;  // detection entries per frame
+  int detect_bins = kDetectBinsPerCta;  // bins per K2 CTA (DetectArgs::bins_per_cta)
+  int wanted_capacity = 0;  // > slot_capacity after a push overflowed: applied by grow_capacity() before the next push
   bool async_mode = false;
 
   SpectralTables tables;
@@ -107,8 +109,7 @@ struct b2s_band : public DeviceQueries {
   Tracker tracker;
 
   // result of the most recently finished chunk (the mailbox) + statistics since the last sync
-  b2s_transmission mailbox[B2S_MAX_TX];
-  int mailbox_count = 0;
+  std::vector<b2s_transmission> mailbox;  // the complete list, strongest first
   int stat_entries = 0, stat_rows = 0;
 
   // profiling
@@ -243,7 +244,11 @@ struct b2s_band : public DeviceQueries {
     a.out_value = d_wq_val.p;
     a.out_index = d_wq_idx.p;
     const size_t smem = sizeof(float) * 2 * max_width;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_window_query, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    {  // a window of up to 4096 bins plus the boxcar halos: opt in once per device
+      int rc2 = prepare_kernel(engine, k_window_query, 256, 64 * 1024, nullptr);
+      if (rc2) return rc2;
+      if (smem > 64 * 1024) return fail(B2S_E_INVALID, "window query of %zu bytes exceeds the kernel's shared-memory budget", smem);
+    }
     cudaEvent_t w0 = nullptr, w1 = nullptr;
     if (profiling) {
       CU(cudaEventCreate(&w0));
@@ -283,7 +288,10 @@ struct b2s_band : public DeviceQueries {
     cfg = c;
     CU(cudaSetDevice(e->device));
     max_frames = c.max_frames_per_push > 0 ? c.max_frames_per_push : 4096;
-    slot_capacity = c.detect_capacity > 0 ? c.detect_capacity : 256;
+    // detection entries kept per frame: every bin of a wideband emitter is one (a 200 kHz FM carrier at 250 Hz/bin is 800), so the
+    // default scales with N; an overflowing push still completes on the truncated lists, reports B2S_E_OVERFLOW and the
+    // capacity grows before the next push (grow_capacity)
+    slot_capacity = c.detect_capacity > 0 ? c.detect_capacity : std::max(256, std::min(4096, c.fft_size / 8));
     async_mode = (c.flags & B2S_FLAG_ASYNC) != 0;
     center = c.center_hz;
     CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
@@ -294,15 +302,25 @@ struct b2s_band : public DeviceQueries {
     cfg.window_taps = nullptr;
     const size_t n = c.fft_size, Y = c.grouping_y;
     const int n_slots = async_mode ? kPushSlots : 1;
+    // K2's CTA width: 112 bins put N = 16384 on 147 SMs (128 would use 128 of the 148); a spectrogram column of d raw bins must not
+    // straddle two CTAs, and the halo has to fit the SUM warps' columns
+    {
+      const int d = c.spectrogram_out_size > 0 ? c.fft_size / c.spectrogram_out_size : 1;
+      const int hp = (c.grouping_x / 2 + 3) & ~3;
+      detect_bins = (112 % d == 0 && 112 + 2 * hp <= kSumThreads) ? 112 : kDetectBinsPerCta;
+      if (const char* e = getenv("B2S_K2_BINS")) detect_bins = atoi(e) == 112 && 112 % d == 0 ? 112 : kDetectBinsPerCta;  // A/B measurements
+      if (detect_bins + 2 * hp > kSumThreads) return fail(B2S_E_INVALID, "grouping_x %d needs a halo of %d bins per side; one K2 CTA holds at most %d columns", c.grouping_x, hp, kSumThreads);
+    }
     for (int i = 0; i < n_slots; ++i) {
       PushSlot& s = slots[i];
       if ((rc = s.psd.alloc(static_cast<size_t>(max_frames) * n))) return rc;
       {
         const int hp = (c.grouping_x / 2 + 3) & ~3;
-        if ((rc = make_tile_map(&s.psd_map, s.psd.p, n, max_frames, kDetectBinsPerCta + 2 * hp, kDetectTileFrames))) return rc;
+        if ((rc = make_tile_map(&s.psd_map, s.psd.p, n, max_frames, detect_bins + 2 * hp, kDetectTileFrames))) return rc;
       }
       if ((rc = s.peak_idx.alloc(max_frames))) return rc;
       if ((rc = s.peak_val.alloc(max_frames))) return rc;
+      if (tables.split > 1 && (rc = s.peak_packed.alloc(max_frames))) return rc;
       if ((rc = s.ckpt.alloc((static_cast<size_t>(max_frames) / kCheckpointEvery + 1) * n))) return rc;
       if ((rc = s.sorted.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
       if ((rc = s.offsets.alloc(max_frames + 1))) return rc;
@@ -366,6 +384,22 @@ struct b2s_band : public DeviceQueries {
     return 0;
   }
 
+  // after an overflow: enlarge the per-frame entry lists (no chunk may be in flight)
+  int grow_capacity() {
+    if (wanted_capacity <= slot_capacity) return 0;
+    int rc = drain();
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    const int cap = std::min(cfg.fft_size, wanted_capacity);
+    const int n_slots = async_mode ? kPushSlots : 1;
+    for (int i = 0; i < n_slots; ++i) {
+      if ((rc = slots[i].sorted.alloc(static_cast<size_t>(max_frames) * cap))) return rc;
+    }
+    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * cap))) return rc;
+    slot_capacity = cap;
+    return 0;
+  }
+
   // ---- worker ----
   void worker_loop() {
     cudaSetDevice(engine->device);
@@ -420,9 +454,40 @@ struct b2s_band : public DeviceQueries {
     return 0;
   }
 
+  // Longest prefix of `frames` frames starting at push frame `frame_offset` during which at most kMaxSpecEmits spectrogram rows
+  // complete (Spectrogram::send fires on the first frame later than last_send + interval, spectrogram.cpp:62-64). Pure: the
+  // slot's clock state is only advanced by enqueue_chunk.
+  size_t emit_limited_length(int64_t t0_ms, double period_ms, size_t frame_offset, size_t frames) const {
+    if (cfg.spectrogram_out_size <= 0) return frames;
+    int64_t last_send = host::frame_time(t0_ms, period_ms, frame_offset);  // a new centre starts its clock on its first frame
+    auto it = spectro.find(center);
+    if (it != spectro.end()) last_send = it->second.last_send;
+    int emits = 0;
+    for (size_t t = 0; t < frames; ++t) {
+      const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
+      if (last_send + cfg.spectrogram_interval_ms < now) {
+        if (emits == kMaxSpecEmits) return t;
+        ++emits;
+        last_send = now;
+      }
+    }
+    return frames;
+  }
+
   int enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out);
   int finish_chunk(PushSlot& s);
   int push_chunk(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
+    // a chunk may complete at most kMaxSpecEmits spectrogram rows (they travel as kernel arguments): cut it there
+    const size_t stride_bytes = static_cast<size_t>(cfg.frame_stride_samples) * (cfg.iq_format == B2S_IQ_CS8 ? 2 : 8);
+    for (size_t done = 0; done < frames;) {
+      const size_t len = emit_limited_length(t0_ms, period_ms, frame_offset + done, frames - done);
+      int rc = push_piece(static_cast<const char*>(iq_dev) + done * stride_bytes, len, t0_ms, period_ms, frame_offset + done, out);
+      if (rc) return rc;
+      done += len;
+    }
+    return 0;
+  }
+  int push_piece(const void* iq_dev, size_t frames, int64_t t0_ms, double period_ms, size_t frame_offset, b2s_result* out) {
     const int idx = async_mode ? next_slot : 0;
     int rc = wait_slot_free(idx);
     if (rc) return rc;
@@ -463,8 +528,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   sa.iq = iq_dev;
   sa.frame_stride_bytes = static_cast<long long>(cfg.frame_stride_samples) * bytes_per_sample;
   sa.n_frames = T;
-  sa.wscale = tables.wscale.p;
-  sa.twiddle = tables.twiddle.p;
+  tables.fill(sa);
+  sa.peak_packed = s.peak_packed.p;
   sa.inv_fs = 1.0f / static_cast<float>(cfg.sample_rate_hz);
   sa.psd_db = s.psd.p;
   sa.power_lin = nullptr;
@@ -494,7 +559,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
       const int64_t now = host::frame_time(t0_ms, period_ms, frame_offset + t);
       ss->counter++;
       if (ss->last_send + cfg.spectrogram_interval_ms < now) {
-        if (n_emit >= kMaxSpecEmits) return fail(B2S_E_INVALID, "more than %d spectrogram rows fall into one push chunk; push fewer frames or raise the interval", kMaxSpecEmits);
+        if (n_emit >= kMaxSpecEmits) return fail(B2S_E_STATE, "internal: chunk not cut at the spectrogram emission limit");  // push_chunk cuts chunks with emit_limited_length
         emit_frames[n_emit] = t;
         emit_divs[n_emit] = ss->counter;
         ++n_emit;
@@ -554,7 +619,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.spec_rows = s.spec_rows.p;
   da.cta_ns = nullptr;
   if (profiling && profile_ctas) {
-    if ((rc = s.cta_ns.alloc(2 * ((n + kDetectBinsPerCta - 1) / kDetectBinsPerCta)))) return rc;
+    if ((rc = s.cta_ns.alloc(2 * ((n + detect_bins - 1) / detect_bins)))) return rc;
     da.cta_ns = s.cta_ns.p;
   }
   da.dense_q = s.dense_q_on ? s.dense_q.p : nullptr;
@@ -563,20 +628,17 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   {
     const int half = cfg.grouping_x / 2;
     const int hp = (half + 3) & ~3;
-    const int width = kDetectBinsPerCta + 2 * hp;
+    const int width = detect_bins + 2 * hp;
+    da.bins_per_cta = detect_bins;
     constexpr size_t kSmemBudget = 220 * 1024;
     const size_t fixed = sizeof(float) * (kAvgBuffers * width * (kDetectTileFrames + 1) + kBoxGroups * kDetectBinsPerCta * kDetectTileFrames);
     const size_t per_tile = sizeof(float) * kDetectTileFrames * width;
     da.n_buffers = static_cast<int>(std::min<size_t>(kDetectBuffers, (kSmemBudget - fixed) / per_tile));
     if (const char* e = getenv("B2S_K2_BUFFERS")) da.n_buffers = std::max(2, std::min(da.n_buffers, atoi(e)));  // experiments
     const size_t smem = fixed + per_tile * da.n_buffers;
-    const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
-    static bool configured = false;
-    if (!configured) {
-      CU(cudaFuncSetAttribute(k_detect<21, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      CU(cudaFuncSetAttribute(k_detect<0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      configured = true;
-    }
+    const int grid = (n + detect_bins - 1) / detect_bins;
+    if ((rc = prepare_kernel(engine, k_detect<21, 10>, kDetectThreads, 220 * 1024, nullptr))) return rc;
+    if ((rc = prepare_kernel(engine, k_detect<0, -1>, kDetectThreads, 220 * 1024, nullptr))) return rc;
     if (profiling) CU(cudaEventRecord(s.ev[2], stream));
     if (half == 10 && Y == 21) {
       k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);
@@ -643,7 +705,7 @@ int b2s_band::finish_chunk(PushSlot& s) {
     CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
     prof.detect_ms += ms;
     if (profile_ctas && s.cta_ns.p) {
-      const int grid = (n + kDetectBinsPerCta - 1) / kDetectBinsPerCta;
+      const int grid = (n + detect_bins - 1) / detect_bins;
       std::vector<unsigned long long> ns(2 * grid);
       CU(cudaMemcpyAsync(ns.data(), s.cta_ns.p, sizeof(unsigned long long) * ns.size(), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -655,7 +717,8 @@ int b2s_band::finish_chunk(PushSlot& s) {
     }
   }
   const auto host_t0 = std::chrono::steady_clock::now();
-  if (*h_max > slot_capacity) return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries; detect_capacity is %d per frame", *h_max, slot_capacity);
+  const bool overflow = *h_max > slot_capacity;  // the push completes on the truncated lists (device and host state stay in step); reported below
+  if (overflow) wanted_capacity = std::max(wanted_capacity, 2 * *h_max);
   if (n_entries > 0) {
     if ((rc = s.h_entries.alloc(n_entries))) return rc;
     CU(cudaMemcpyAsync(s.h_entries.p, s.sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, st));
@@ -675,11 +738,11 @@ int b2s_band::finish_chunk(PushSlot& s) {
   }
   prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 
-  // the mailbox after the last frame of this chunk
-  mailbox_count = 0;
+  // the mailbox after the last frame of this chunk (Notification::notify, transmission.cpp:67)
+  mailbox.clear();
   if (!states.empty() && states.back().frame == T - 1) {
-    const int total = tracker.sorted_transmissions(states.back(), mailbox, B2S_MAX_TX);
-    mailbox_count = std::min(total, B2S_MAX_TX);
+    mailbox.resize(states.back().keys.size());
+    tracker.sorted_transmissions(states.back(), mailbox.data(), static_cast<int>(mailbox.size()));
   }
   stat_entries += n_entries;
   stat_rows += s.n_emit;
@@ -693,8 +756,9 @@ int b2s_band::finish_chunk(PushSlot& s) {
             tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (s.frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
       }
     }
-    out->n_transmissions = mailbox_count;
-    std::memcpy(out->transmissions, mailbox, sizeof(b2s_transmission) * mailbox_count);
+    out->n_transmissions_total = static_cast<int32_t>(mailbox.size());
+    out->n_transmissions = std::min<int32_t>(out->n_transmissions_total, B2S_MAX_TX);
+    std::memcpy(out->transmissions, mailbox.data(), sizeof(b2s_transmission) * out->n_transmissions);
     if (out->peak_index) CU(cudaMemcpyAsync(out->peak_index + s.frame_offset, s.peak_idx.p, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
     if (out->peak_value) CU(cudaMemcpyAsync(out->peak_value + s.frame_offset, s.peak_val.p, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
     const size_t row_bytes = sizeof(float) * static_cast<size_t>(T) * n, off = s.frame_offset * n;
@@ -713,5 +777,8 @@ int b2s_band::finish_chunk(PushSlot& s) {
   }
   CU(cudaStreamSynchronize(st));
   cur = nullptr;
+  if (overflow)
+    return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries but detect_capacity is %d per frame: the frame's list was truncated (the push completed on the "
+                "truncated lists); the capacity grows to %d before the next push", *h_max, slot_capacity, std::min(cfg.fft_size, wanted_capacity));
   return 0;
 }

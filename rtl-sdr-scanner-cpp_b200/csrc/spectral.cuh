@@ -161,6 +161,13 @@ struct SpectralArgs {
   float* power_lin;             // optional [n_frames][N] |X|^2 / fs (only read by the DEBUG instantiation)
   int* peak_index;              // [n_frames]
   float* peak_value;            // [n_frames]
+  // ---- k_spectrum3 only ----
+  int* work_counter;            // [2] {next work item, CTAs finished}: dynamic work distribution; both zero between launches
+  // split mode, N = S * 16384 (S = 2..16): CTA-items (frame, c) each produce the bins k = S k' + c of one frame
+  int split;                    // S (1 = off)
+  const float2* split_tw;       // [S][16384]  W_N^(n' c)
+  const float2* split_ws;       // [S]         W_S^j
+  unsigned long long* peak_packed;  // [n_frames], zeroed before the launch: max over the S classes of (ordered(value) << 32 | ~index)
 };
 
 // tw points at this pass's [m-1][k] table (shared or global)

@@ -90,37 +90,125 @@ struct TwiddleLayout3 {
   static constexpr int A = (RA - 1) * 1024, B = 31 * 32, TOTAL = A + B;
 };
 
-template <int RA, int MODE, bool DEBUG_LIN>
+// order-preserving image of a float (atomicMax on the image == max on the floats)
+__device__ __forceinline__ unsigned int ordered_bits(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+constexpr int kSplitM = 16384;          // sub-transform length of the split mode (RA = 16)
+constexpr int kSplitStageBytes = 32768; // one staging buffer: S row segments of 16384 / S int8 pairs each
+
+// Work distribution: items are handed out through an atomic counter (a.work_counter[0]) instead of a fixed
+// blockIdx-strided walk, so a CTA that starts late (another band's kernel still holds its SM, config 3 / 5) simply takes
+// fewer items; the kernel leaves the counter pair zeroed for the next launch.
+//
+// SPLIT (N = S * 16384, S = 2, 4, 8, 16 -> N = 32768 ... 262144): decimation in frequency over the S residue classes of
+// the bin index. Item (frame, c) computes
+//        y_c[n'] = W_N^(n' c) * sum_s x[n' + 16384 s] w[n' + 16384 s] W_S^(s c),     n' < 16384        (pre-pass)
+// and X[S k' + c] = FFT_16384(y_c)[k'] with exactly the passes of the non-split kernel. The S items of one frame are
+// adjacent in the work order: they read the same int8 frame (L2 hits after the first) and fill the same output sectors.
+// The int8 frame reaches the pre-pass through a 2-stage ring of bulk copies (S row segments per stage).
+template <int RA, int MODE, bool DEBUG_LIN, bool SPLIT>
 __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
-  constexpr int N = RA * 1024, T = RA * 32, BPT = 32 / RA;  // threads, pass-A butterflies per thread
+  constexpr int M = RA * 1024, T = RA * 32, BPT = 32 / RA;  // sub-transform length, threads, pass-A butterflies per thread
+  static_assert(!SPLIT || RA == 16, "the split mode runs 16384-point sub-transforms");
   extern __shared__ __align__(128) unsigned char smem[];
   float2* X = reinterpret_cast<float2*>(smem);                                 // [RA][kBlockPitch]
   float2* twB = X + RA * kBlockPitch;                                          // [31][32]
-  unsigned char* raw = reinterpret_cast<unsigned char*>(twB + 31 * 32);        // 2N bytes (TMA mode only)
+  unsigned char* raw = reinterpret_cast<unsigned char*>(twB + 31 * 32);        // TMA mode: 2M bytes, or 2 x kSplitStageBytes (split)
   float* Xf = reinterpret_cast<float*>(X);
-  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ float red_v[32];
   __shared__ int red_i[2];
+  __shared__ int s_item[2];
+  __shared__ float2 s_ws[16];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const char* base = static_cast<const char*>(a.iq);
   const float2* twA = a.twiddle;
+  const int S = SPLIT ? a.split : 1;
+  const int N = S * M;
+  const int n_items = a.n_frames * S;
+  const int pc = SPLIT ? M / S : M;  // samples per row segment of a stage
 
   if (MODE == kModeCs8Tma && tid == 0) {
-    mbar_init(&full_bar, 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
     fence_barrier_init();
   }
+  if (tid == 0) s_item[0] = atomicAdd(a.work_counter, 1);
   for (int i = tid; i < 31 * 32; i += T) twB[i] = a.twiddle[TwiddleLayout3<RA>::A + i];
   __syncthreads();
-  if (MODE == kModeCs8Tma && tid == 0 && static_cast<int>(blockIdx.x) < a.n_frames) {
-    mbar_arrive_expect_tx(&full_bar, 2 * N);
-    bulk_g2s(raw, base + static_cast<long long>(blockIdx.x) * a.frame_stride_bytes, 2 * N, &full_bar);
+  int item = s_item[0];
+
+  // stage `q`-th chunk of `it_`: S segments [s][pc samples] of the frame (split) / the whole frame (non-split)
+  auto issue = [&](int it_, int q, int stage) {
+    if (SPLIT) {
+      const int fr = it_ / S;
+      const char* src = base + static_cast<long long>(fr) * a.frame_stride_bytes + static_cast<long long>(q) * pc * 2;
+      mbar_arrive_expect_tx(&full_bar[stage], kSplitStageBytes);
+      for (int s = 0; s < S; ++s) bulk_g2s(raw + stage * kSplitStageBytes + s * pc * 2, src + static_cast<long long>(s) * M * 2, pc * 2, &full_bar[stage]);
+    } else {
+      mbar_arrive_expect_tx(&full_bar[0], 2 * M);
+      bulk_g2s(raw, base + static_cast<long long>(it_) * a.frame_stride_bytes, 2 * M, &full_bar[0]);
+    }
+  };
+  if (MODE == kModeCs8Tma && tid == 0 && item < n_items) {
+    issue(item, 0, 0);
+    if (SPLIT) issue(item, 1, 1);
   }
 
-  uint32_t parity = 0;
-  for (int frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
-    // ---------------- pass A: radix RA over n0 (stride 1024), input = windowed int8 samples ----------------
-    if (MODE == kModeCs8Tma) mbar_wait(&full_bar, parity);
+  uint32_t parity = 0;   // non-split: phase of full_bar[0]
+  uint32_t chunk_no = 0; // split: chunks consumed so far by this CTA (stage = chunk_no & 1, phase = (chunk_no >> 1) & 1)
+  int round = 0;
+  while (item < n_items) {
+    const int frame = SPLIT ? item / S : item;
+    const int c = SPLIT ? item - frame * S : 0;
+    if (tid == 0) s_item[(round + 1) & 1] = atomicAdd(a.work_counter, 1);  // the item after this one (read after the next barrier)
+    if (SPLIT) {
+      // ---------------- pre-pass: y_c into the exchange buffer, laid out like pass A's input [m][b] ----------------
+      if (tid < S) s_ws[tid] = a.split_ws[(tid * c) & (S - 1)];
+      __syncthreads();
+      const float2* twc = a.split_tw + static_cast<size_t>(c) * M;
+      for (int q = 0; q < S; ++q) {
+        const unsigned char* st = raw + (chunk_no & 1u) * kSplitStageBytes;
+        if (MODE == kModeCs8Tma) mbar_wait(&full_bar[chunk_no & 1u], (chunk_no >> 1) & 1u);
+        for (int i = tid; i < pc; i += T) {
+          const int np = q * pc + i;
+          float2 acc = make_float2(0.0f, 0.0f);
+          for (int s = 0; s < S; ++s) {
+            const int n = np + s * M;
+            const float w = __ldg(&a.wscale[n]);
+            float2 xs;
+            if (MODE == kModeCs8Tma) {
+              const char2 smp = reinterpret_cast<const char2*>(st + s * pc * 2)[i];
+              xs = make_float2(static_cast<float>(smp.x) * w, static_cast<float>(smp.y) * w);
+            } else if (MODE == kModeCs8Direct) {
+              const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+              xs = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+            } else {
+              const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+              xs = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+            }
+            const float2 ws = s_ws[s];
+            acc.x = fmaf(xs.x, ws.x, fmaf(-xs.y, ws.y, acc.x));
+            acc.y = fmaf(xs.x, ws.y, fmaf(xs.y, ws.x, acc.y));
+          }
+          if (c != 0) acc = cmul(acc, __ldg(&twc[np]));
+          X[(np >> 10) * kBlockPitch + (np & 1023)] = acc;
+        }
+        __syncthreads();  // this stage is consumed (and, after the last chunk, y_c is complete)
+        if (MODE == kModeCs8Tma && tid == 0) {  // refill it with the chunk two ahead (possibly of the next item)
+          const int next = s_item[(round + 1) & 1];
+          if (q + 2 < S) issue(item, q + 2, chunk_no & 1u);
+          else if (next < n_items) issue(next, q + 2 - S, chunk_no & 1u);
+        }
+        ++chunk_no;
+      }
+    }
+    // ---------------- pass A: radix RA over n0 (stride 1024), input = windowed int8 samples (or y_c) ----------------
+    if (!SPLIT && MODE == kModeCs8Tma) mbar_wait(&full_bar[0], parity);
     parity ^= 1;
 #pragma unroll
     for (int u = 0; u < BPT; ++u) {
@@ -129,16 +217,20 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
 #pragma unroll
       for (int m = 0; m < RA; ++m) {
         const int n = m * 1024 + b;
-        const float w = __ldg(&a.wscale[n]);
-        if (MODE == kModeCs8Tma) {
-          const char2 s = reinterpret_cast<const char2*>(raw)[n];
-          v[m] = make_float2(static_cast<float>(s.x) * w, static_cast<float>(s.y) * w);
-        } else if (MODE == kModeCs8Direct) {
-          const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-          v[m] = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+        if (SPLIT) {
+          v[m] = X[m * kBlockPitch + b];  // in place: this thread alone reads and writes column b of every block
         } else {
-          const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-          v[m] = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+          const float w = __ldg(&a.wscale[n]);
+          if (MODE == kModeCs8Tma) {
+            const char2 s = reinterpret_cast<const char2*>(raw)[n];
+            v[m] = make_float2(static_cast<float>(s.x) * w, static_cast<float>(s.y) * w);
+          } else if (MODE == kModeCs8Direct) {
+            const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+            v[m] = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+          } else {
+            const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
+            v[m] = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+          }
         }
       }
       Dft<RA>::run(v);
@@ -147,13 +239,8 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
       for (int k0 = 1; k0 < RA; ++k0) X[k0 * kBlockPitch + b] = cmul(v[k0], __ldg(&twA[(k0 - 1) * 1024 + b]));
     }
     __syncthreads();
-    if (MODE == kModeCs8Tma && tid == 0) {  // staging buffer consumed: fetch this CTA's next frame behind the remaining passes
-      const int next = frame + gridDim.x;
-      if (next < a.n_frames) {
-        mbar_arrive_expect_tx(&full_bar, 2 * N);
-        bulk_g2s(raw, base + static_cast<long long>(next) * a.frame_stride_bytes, 2 * N, &full_bar);
-      }
-    }
+    const int next_item = s_item[(round + 1) & 1];
+    if (!SPLIT && MODE == kModeCs8Tma && tid == 0 && next_item < n_items) issue(next_item, 0, 0);  // staging buffer consumed: fetch the next frame behind the remaining passes
     // ---------------- passes B and C: warp `warp` owns block k0 = warp ----------------
     float2 v[32];
     float2* blk = X + warp * kBlockPitch;
@@ -186,14 +273,14 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     if (lane == 0) red_v[warp] = best_v;
     if (tid == 0) red_i[0] = 0x7fffffff;
     __syncthreads();
-    // ---------------- output: 4 consecutive bins per thread, 16-byte coalesced stores at (bin + N/2) mod N ----------------
+    // ---------------- output: 4 consecutive (local) bins per thread, stored at (bin + N/2) mod N ----------------
     float row_max = red_v[0];
 #pragma unroll
     for (int w = 1; w < RA; ++w) row_max = fmaxf(row_max, red_v[w]);
     float* row = a.psd_db + static_cast<size_t>(frame) * N;
     int best_i = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < N / (4 * T); ++i) {
+    for (int i = 0; i < M / (4 * T); ++i) {
       const int bin = 4 * (tid + i * T);
       const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
       const int k0 = bin & (RA - 1);
@@ -203,27 +290,67 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
       o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
       o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
       o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
-      const int j = (bin + N / 2) & (N - 1);
+      const int jl = (bin + M / 2) & (M - 1);  // local fftshift; the S classes interleave: global bin = S * local + c
       if (DEBUG_LIN) {  // debug instantiation: the block holds |X|^2/fs; dB is recomputed here
-        *reinterpret_cast<float4*>(a.power_lin + static_cast<size_t>(frame) * N + j) = o;
+        float* lin = a.power_lin + static_cast<size_t>(frame) * N;
+        if (SPLIT) {
+          lin[S * jl + c] = o.x;
+          lin[S * (jl + 1) + c] = o.y;
+          lin[S * (jl + 2) + c] = o.z;
+          lin[S * (jl + 3) + c] = o.w;
+        } else {
+          *reinterpret_cast<float4*>(lin + jl) = o;
+        }
         o.x = kDbPerLog2 * fast_log2(o.x);
         o.y = kDbPerLog2 * fast_log2(o.y);
         o.z = kDbPerLog2 * fast_log2(o.z);
         o.w = kDbPerLog2 * fast_log2(o.w);
       }
-      *reinterpret_cast<float4*>(row + j) = o;
+      if (SPLIT) {
+        row[S * jl + c] = o.x;
+        row[S * (jl + 1) + c] = o.y;
+        row[S * (jl + 2) + c] = o.z;
+        row[S * (jl + 3) + c] = o.w;
+      } else {
+        *reinterpret_cast<float4*>(row + jl) = o;
+      }
+      const int j = SPLIT ? S * jl + c : jl;
       if (o.x == row_max) best_i = min(best_i, j);
-      if (o.y == row_max) best_i = min(best_i, j + 1);
-      if (o.z == row_max) best_i = min(best_i, j + 2);
-      if (o.w == row_max) best_i = min(best_i, j + 3);
+      if (o.y == row_max) best_i = min(best_i, j + S);
+      if (o.z == row_max) best_i = min(best_i, j + 2 * S);
+      if (o.w == row_max) best_i = min(best_i, j + 3 * S);
     }
     if (best_i != 0x7fffffff) atomicMin(&red_i[0], best_i);
     __syncthreads();  // the exchange buffer is free again; red_i is final
     if (tid == 0) {
-      a.peak_index[frame] = red_i[0];
-      a.peak_value[frame] = row_max;
+      if (SPLIT) {  // first maximum over the S classes: larger value wins, equal values -> lower index
+        atomicMax(a.peak_packed + frame, (static_cast<unsigned long long>(ordered_bits(row_max)) << 32) | (0xffffffffu - static_cast<unsigned int>(red_i[0])));
+      } else {
+        a.peak_index[frame] = red_i[0];
+        a.peak_value[frame] = row_max;
+      }
+    }
+    item = next_item;
+    ++round;
+  }
+  // leave the counters zeroed for the next launch: the last CTA to get here resets them (every CTA has drawn its last item)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(a.work_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      a.work_counter[0] = 0;
+      a.work_counter[1] = 0;
     }
   }
+}
+
+// split mode: (value, index) out of the packed per-frame maxima
+__global__ void k_peak_unpack(const unsigned long long* packed, int n_frames, int* peak_index, float* peak_value) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const unsigned long long p = packed[f];
+  const unsigned int u = static_cast<unsigned int>(p >> 32);
+  peak_value[f] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+  peak_index[f] = static_cast<int>(0xffffffffu - static_cast<unsigned int>(p & 0xffffffffu));
 }
 
 }  // namespace b2s

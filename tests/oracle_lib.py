@@ -295,6 +295,19 @@ class OracleChain:
         ready = self.L.orc_chain_get_noise(self.h, _p(thr), C.byref(samples))
         return thr, samples.value, bool(ready)
 
+    def get_signals(self, cap=4096):
+        keys, first, last, power = np.zeros(cap, np.int32), np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.float32)
+        self.L.orc_chain_get_signals.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int]
+        k = min(self.L.orc_chain_get_signals(self.h, _p(keys), _p(first), _p(last), _p(power), cap), cap)
+        return keys[:k], first[:k], last[:k], power[:k]
+
+    def get_transmissions(self, cap=4096):
+        """The complete sorted list after the most recent frame: [(shift_hz, flush, key, power)]."""
+        f, fl, key, pw = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        self.L.orc_chain_get_transmissions.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int]
+        k = min(self.L.orc_chain_get_transmissions(self.h, _p(f), _p(fl), _p(key), _p(pw), cap), cap)
+        return [(int(f[i]), int(fl[i]), int(key[i]), float(pw[i])) for i in range(k)]
+
     def get_spectrogram(self, cap=64):
         m = max(self.cfg.spectrogram_out_size, 1)
         times = np.zeros(cap, dtype=np.int64)

@@ -34,9 +34,10 @@ def _noise_tones(n, frames, seed, stride=None):
     return synth.make_iq_int8(n, frames, tones, seed=seed, stride=stride)
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144])
 def test_psd_rows_match_oracle(engine, n):
-    frames = 6
+    """N <= 2048: k_spectrum; 4096..16384: k_spectrum3; 32768..262144: k_spectrum3's split mode (S = N/16384 residue classes)."""
+    frames = 6 if n <= 16384 else 3
     fs = 20_000_000 if n >= 8192 else 2_048_000
     cfg = b2s.make_config(n, fs)
     iq = _noise_tones(n, frames, seed=n)
@@ -50,6 +51,18 @@ def test_psd_rows_match_oracle(engine, n):
     print(f"\nN={n}: floored pass {st['pass_frac']:.5f} worst {st['worst']:.2e} strict pass {st['strict_frac']:.4f} L2rel {st['l2_rel']:.2e}")
     assert st["pass_frac"] >= 0.995 and st["worst"] <= 1e-4 and st["l2_rel"] <= 1e-6, st
     assert np.array_equal(np.argmax(psd, axis=1), np.argmax(ref, axis=1))
+
+
+@pytest.mark.parametrize("n", [4096, 32768, 262144])
+def test_psd_peaks_through_the_band(engine, n):
+    """peak_index / peak_value (first maximum of the raw row, noise_learner.cpp:53-59): with the split mode the S residue classes of
+    a frame are reduced through a packed atomic maximum."""
+    fs, frames = 20_000_000, 5
+    cfg = b2s.make_config(n, fs, learn_frames=2, spectrogram_out_size=0, max_frames_per_push=8)
+    iq = _noise_tones(n, frames, seed=n + 1)
+    got = b2s.Band(engine, cfg).push(iq, frames, 0, 1.0, per_frame=True, dense=("psd_db",))
+    assert np.array_equal(got.peak_index, np.argmax(got.psd_db, axis=1))
+    assert np.array_equal(got.peak_value, got.psd_db.max(axis=1))
 
 
 def test_psd_known_answers_on_gpu(engine):
@@ -68,14 +81,21 @@ def test_psd_known_answers_on_gpu(engine):
     assert int(np.argmax(p[2])) == 3 * n // 4
 
 
-def test_psd_input_variants(engine):
-    """CF32 input, decimated frames (stride r*N) and a stride that defeats the 16-byte TMA path all give the same rows."""
-    n, fs, frames = 2048, 2_048_000, 5
+@pytest.mark.parametrize("n", [2048, 8192, 16384, 32768, 131072])
+def test_psd_input_variants(engine, n):
+    """CF32 input, decimated frames (stride r*N) and a stride that defeats the 16-byte TMA path all give the same rows — for
+    k_spectrum (2048), k_spectrum3's three load modes (8192, 16384) and the split mode's pre-pass (32768, 131072)."""
+    fs, frames = 2_048_000, 5 if n <= 16384 else 3
     iq = _noise_tones(n, frames, seed=3)
     base = engine.psd(b2s.make_config(n, fs), iq, frames)
+    ref = np.stack([ol.oracle_psd_frame(b2s.make_config(n, fs), iq[k * 2 * n : (k + 1) * 2 * n]) for k in range(frames)])
+    ol.assert_db_rows_close(base, ref, f"cs8 N={n}")
     f32 = (iq.astype(np.float32) * np.float32(1 / 127.0)).astype(np.float32)
-    cf = engine.psd(b2s.make_config(n, fs, iq_format=b2s.IQ_CF32), f32, frames)
+    cfg_f = b2s.make_config(n, fs, iq_format=b2s.IQ_CF32)
+    cf = engine.psd(cfg_f, f32, frames)
     ol.assert_db_rows_close(cf, base, "cf32 vs cs8")  # only the unpack rounding differs (scale folded into the window for CS8)
+    ref_f = np.stack([ol.oracle_psd_frame(cfg_f, f32[k * 2 * n : (k + 1) * 2 * n]) for k in range(frames)])
+    ol.assert_db_rows_close(cf, ref_f, f"cf32 N={n} vs oracle")
     # decimator: keep the first N samples of every 3N (decimator.h:16-22)
     wide = np.zeros((frames, 3 * n * 2), np.int8)
     wide[:, : 2 * n] = iq.reshape(frames, 2 * n)
@@ -189,7 +209,8 @@ def _run_both(engine, cfg, iq, frames, period, t0=0, splits=None):
     raise NotImplementedError
 
 
-@pytest.mark.parametrize("n,fs,frames,learn", [(1024, 2_048_000, 400, 40), (4096, 2_048_000, 260, 30), (256, 2_048_000, 300, 30)])
+@pytest.mark.parametrize("n,fs,frames,learn", [(1024, 2_048_000, 400, 40), (4096, 2_048_000, 260, 30), (256, 2_048_000, 300, 30),
+                                               (8192, 2_048_000, 400, 40), (32768, 20_000_000, 400, 40)])
 def test_band_matches_oracle_end_to_end(engine, n, fs, frames, learn):
     cfg, tones, iq, period = scene(n, fs, frames, learn)
     band, got, ref = _run_both(engine, cfg, iq, frames, period, t0=1000)
@@ -457,3 +478,104 @@ def test_invalid_arguments_return_codes_not_crashes(engine):
     with pytest.raises(b2s.B2SError) as e:
         band.push(iq, 120, 0, period)
     assert "b2s error -4" in str(e.value)  # B2S_E_OVERFLOW, loud — not a silent truncation
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the benchmark's own scene, N = 32768 chains, several engines, exact constant division
+# ------------------------------------------------------------------------------------------------------------
+def _bench_scene(n, fs, frames, learn, seed):
+    import bench
+
+    tones = bench.bench_tones(synth, n, frames, learn)
+    return synth.make_iq_int8(n, frames, tones, seed=seed, quiet_frames=learn)
+
+
+def _mailbox(res):
+    return [(t.shift_hz, t.flush, t.key) for t in res.transmissions[: res.n_transmissions]]
+
+
+def test_bench_scene_matches_oracle_async(engine):
+    """bench.py's workload through the path bench.py times: N = 16384, fs = 20 MS/s, reference levels / time-outs, B2S_FLAG_ASYNC,
+    device-resident IQ, two pushes of 2048 frames (the second starts with live signals). Mailbox after every push, live signal
+    map and noise threshold against the oracle; Averager state bit-exact against an oracle Averager fed the engine's own rows."""
+    import torch
+
+    n, fs, frames, learn = 16384, 20_000_000, 2048, 100
+    period = synth.frame_period_ms(n, fs)
+    iq = _bench_scene(n, fs, frames, learn, synth.seed_for(2))
+    cfg = b2s.make_config(n, fs, learn_frames=learn, max_frames_per_push=frames, flags=b2s.FLAG_ASYNC | b2s.FLAG_IQ_ON_DEVICE)
+    band = b2s.Band(engine, cfg)
+    ocfg = b2s.make_config(n, fs, learn_frames=learn)
+    o = ol.OracleChain(ocfg)
+    iq_dev = torch.from_numpy(iq).cuda()
+    t0 = 0
+    for rep in range(2):
+        band.push_raw(iq_dev.data_ptr(), frames, t0, period)
+        res = band.sync()
+        ref = o.push(iq, frames, t0, period, dense=())
+        assert _mailbox(res) == [(f, fl, k) for f, fl, k, _ in ref.frame_tx[-1]], rep
+        assert res.n_detect_entries > 1000
+        t0 += int(frames * period)
+    keys_g, first_g, last_g, _ = band.get_signals()
+    keys_o, first_o, last_o, _ = o.get_signals()
+    assert np.array_equal(keys_g, keys_o) and np.array_equal(first_g, first_o) and np.array_equal(last_g, last_o)
+    thr_g, _, ready_g = band.get_noise()
+    thr_o, _, ready_o = o.get_noise()
+    assert ready_g and ready_o and np.max(np.abs(thr_g - thr_o)) <= 2e-3
+    # Averager state: bit-exact on identical rows (a synchronous twin provides the rows of the second push)
+    twin = b2s.Band(engine, b2s.make_config(n, fs, learn_frames=learn, max_frames_per_push=frames))
+    twin.push(iq, frames, 0, period)
+    got = twin.push(iq[: 64 * 2 * n], 64, int(frames * period), period, dense=("noise_sub_db",))
+    band.push_raw(iq_dev.data_ptr(), 64, t0, period)
+    band.sync()
+    for a, b in zip(band.get_averager(), twin.get_averager()):
+        assert np.array_equal(a, b)
+    cpu = ol.CpuAverager(n, 21, "orc")
+    for r in got.noise_sub_db[-21:]:
+        cpu.push(r)
+    s_, a_, ring, f = band.get_averager()
+    assert ring.tobytes() == cpu.data().tobytes() and f == 21
+
+
+def test_two_engines_in_one_process(engine):
+    """Function attributes (opt-in shared memory) are per device: a second engine — on another GPU when the box has one, else on
+    the same — must be able to launch the large-shared-memory kernels, and gives the same result."""
+    import torch
+
+    dev = 1 if torch.cuda.device_count() > 1 else 0
+    other = b2s.Engine(dev)
+    n, fs, frames, learn = 16384, 20_000_000, 160, 30
+    cfg = b2s.make_config(n, fs, learn_frames=learn, min_time_ms=20, timeout_ms=30)
+    iq = synth.make_iq_int8(n, frames, synth.standard_scene(n, frames, learn), seed=5, quiet_frames=learn)
+    period = synth.frame_period_ms(n, fs)
+    a = b2s.Band(engine, cfg).push(iq, frames, 0, period, per_frame=True, dense=("psd_db",))
+    b = b2s.Band(other, cfg).push(iq, frames, 0, period, per_frame=True, dense=("psd_db",))
+    assert np.array_equal(a.psd_db, b.psd_db) and _tx(a.frame_tx) == _tx(b.frame_tx) and sum(len(x) for x in a.frame_tx) > 20
+    other.close()
+
+
+def test_exact_constant_division_exhaustive(engine):
+    """div_const<D> (detect.cuh, Markstein's 3-instruction sequence) against IEEE division for EVERY float with an exponent in the
+    guarded range [2^-60, 2^60], both signs, D = 21 (GROUPING_X = GROUPING_Y) and the other divisors the fast paths use."""
+    for d in (21, 2, 3, 5, 7, 9, 11, 13, 15, 17, 19):
+        bad = engine.check_div_const(d)
+        assert bad == 0, (d, bad)
+
+
+def test_more_signals_than_the_result_struct_holds(engine):
+    """The signal map is not limited to B2S_MAX_TX (the reference's std::map is unbounded): 80 simultaneous carriers are all
+    tracked; the embedded array holds the 64 strongest and says so, b2s_band_get_transmissions returns the whole list."""
+    n, fs, frames, learn = 8192, 8_192_000, 80, 20
+    tones = [synth.Tone(-3900.1 + 97 * i, amplitude=30.0 + (i % 7), fm_dev_bins=3.0) for i in range(80)]
+    iq = synth.make_iq_int8(n, frames, tones, seed=9, quiet_frames=learn)
+    cfg = b2s.make_config(n, fs, learn_frames=learn, group_size_bins=16, min_time_ms=10, timeout_ms=30)
+    band = b2s.Band(engine, cfg)
+    period = synth.frame_period_ms(n, fs)
+    res = band.push_raw(iq.ctypes.data, frames, 0, period)
+    o = ol.OracleChain(cfg)
+    o.push(iq, frames, 0, period, dense=())
+    want = [(f, fl, k) for f, fl, k, _ in o.get_transmissions()]
+    assert len(want) >= 70
+    assert res.n_transmissions_total == len(want) and res.n_transmissions == b2s.MAX_TX
+    assert [(f, fl, k) for f, fl, k, _ in band.get_transmissions()] == want
+    assert _mailbox(res) == want[: b2s.MAX_TX]
