@@ -156,12 +156,14 @@ typedef struct b2s_profile {
   double spectral_ms;        /* K1 k_spectrum: unpack+window+FFT+PSD */
   double detect_ms;          /* K2 k_detect: noise/averager/boxcar/threshold/spectrogram */
   double window_ms;          /* K3 k_window_query (only when the tracker needs sub-threshold window maxima) */
-  double tracker_host_ms;    /* host bookkeeping (wall clock) */
+  double tracker_host_ms;    /* host time spent on the results of a push (wall clock): reading K4's result, or tracker.h when every frame's list is wanted */
   int64_t spectral_launches, detect_launches, window_launches;
   int64_t pushes, frames;
   int64_t h2d_bytes, d2h_bytes; /* bytes moved by b2s_band_push itself */
   /* load balance of K2 (one CTA per 128 bins): per-CTA run time in ms, median and slowest, summed over launches */
   double detect_cta_median_ms, detect_cta_max_ms;
+  double track_ms;           /* K4 k_runs + k_track: the signal map on the device (runs beside the next push's K1) */
+  int64_t track_launches;
 } b2s_profile;
 int b2s_band_set_profiling(b2s_band* b, int enable); /* 0 off, 1 kernel times and byte counts, 2 also K2 per-CTA run times */
 int b2s_band_get_profile(b2s_band* b, b2s_profile* out, int reset);

@@ -95,6 +95,8 @@ class Profile(C.Structure):
         ("d2h_bytes", C.c_int64),
         ("detect_cta_median_ms", C.c_double),
         ("detect_cta_max_ms", C.c_double),
+        ("track_ms", C.c_double),
+        ("track_launches", C.c_int64),
     ]
 
 

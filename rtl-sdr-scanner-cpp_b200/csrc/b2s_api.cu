@@ -21,6 +21,7 @@
 #include "detect.cuh"
 #include "host_utils.h"
 #include "spectral3.cuh"
+#include "track.cuh"
 #include "tracker.h"
 
 namespace {
@@ -149,21 +150,23 @@ int launch_spectrum_v(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream)
   return 0;
 }
 // k_spectrum3: N = RA * 1024 directly (RA = 4, 8, 16), or N = S * 16384 through the split mode (S = a.split > 1)
-template <int RA, int MODE, bool LIN, bool SPLIT>
+template <int RA, int MODE, bool LIN, int S>
 int launch_spectrum3_v(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   constexpr int T = RA * 32;
+  constexpr bool SPLIT = S > 1;
   const size_t smem = sizeof(float2) * (RA * kBlockPitch + 31 * 32) + (MODE == kModeCs8Tma ? (SPLIT ? 2 * kSplitStageBytes : 2 * RA * 1024) : 0);
   int ctas_per_sm = 1;
-  int rc = prepare_kernel(e, k_spectrum3<RA, MODE, LIN, SPLIT>, T, smem, &ctas_per_sm);
+  int rc = prepare_kernel(e, k_spectrum3<RA, MODE, LIN, S>, T, smem, &ctas_per_sm);
   if (rc) return rc;
   if (!a.work_counter) return fail(B2S_E_INVALID, "k_spectrum3 needs a work counter");
-  const int items = a.n_frames * (SPLIT ? a.split : 1);
+  const int items = a.n_frames * S;
+  if (a.split != S) return fail(B2S_E_INVALID, "split tables were built for another fft_size");
   const int grid = std::min(items, e->sm_count * ctas_per_sm);
   if (SPLIT) {
     if (!a.peak_packed || !a.split_tw || !a.split_ws) return fail(B2S_E_INVALID, "split-mode tables are missing");
     CU(cudaMemsetAsync(a.peak_packed, 0, sizeof(unsigned long long) * a.n_frames, stream));
   }
-  k_spectrum3<RA, MODE, LIN, SPLIT><<<grid, T, smem, stream>>>(a);
+  k_spectrum3<RA, MODE, LIN, S><<<grid, T, smem, stream>>>(a);
   CU(cudaGetLastError());
   if (SPLIT) {
     k_peak_unpack<<<(a.n_frames + 255) / 256, 256, 0, stream>>>(a.peak_packed, a.n_frames, a.peak_index, a.peak_value);
@@ -181,11 +184,11 @@ template <int N, int MODE>
 int launch_spectrum_t(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream) {
   // the |X|^2/fs debug rows come from a debug twin of each instantiation (parity tests); the product one stays lean
   if constexpr (N > kSplitM) {
-    if (a.power_lin) return launch_spectrum3_v<16, MODE, true, true>(e, a, stream);
-    return launch_spectrum3_v<16, MODE, false, true>(e, a, stream);
+    if (a.power_lin) return launch_spectrum3_v<16, MODE, true, N / kSplitM>(e, a, stream);
+    return launch_spectrum3_v<16, MODE, false, N / kSplitM>(e, a, stream);
   } else if constexpr (k1_is_v3(N)) {
-    if (a.power_lin) return launch_spectrum3_v<N / 1024, MODE, true, false>(e, a, stream);
-    return launch_spectrum3_v<N / 1024, MODE, false, false>(e, a, stream);
+    if (a.power_lin) return launch_spectrum3_v<N / 1024, MODE, true, 1>(e, a, stream);
+    return launch_spectrum3_v<N / 1024, MODE, false, 1>(e, a, stream);
   } else {
     if (a.power_lin) return launch_spectrum_v<N, MODE, true>(e, a, stream);
     return launch_spectrum_v<N, MODE, false>(e, a, stream);
@@ -203,9 +206,10 @@ int launch_spectrum_n(b2s_engine* e, int n, const SpectralArgs& a, cudaStream_t 
     case 4096: return launch_spectrum_t<4096, MODE>(e, a, stream);
     case 8192: return launch_spectrum_t<8192, MODE>(e, a, stream);
     case 16384: return launch_spectrum_t<16384, MODE>(e, a, stream);
-    case 32768: case 65536: case 131072: case 262144:
-      if (a.split != n / kSplitM) return fail(B2S_E_INVALID, "split tables were built for another fft_size");
-      return launch_spectrum_t<2 * kSplitM, MODE>(e, a, stream);  // one instantiation serves every S (a.split)
+    case 32768: return launch_spectrum_t<32768, MODE>(e, a, stream);
+    case 65536: return launch_spectrum_t<65536, MODE>(e, a, stream);
+    case 131072: return launch_spectrum_t<131072, MODE>(e, a, stream);
+    case 262144: return launch_spectrum_t<262144, MODE>(e, a, stream);
     default: return fail(B2S_E_INVALID, "fft_size %d is not supported (256..%d)", n, kMaxFft);
   }
 }
@@ -355,6 +359,17 @@ static int make_tile_map(CUtensorMap* out, const float* base, size_t cols, size_
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2S_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", static_cast<int>(r), box_cols, box_rows);
   return 0;
+}
+
+// Least float x with fl(x / divisor) >= level (IEEE single division is monotonic in x, so the bins whose quotient reaches a level
+// are exactly those whose undivided sum reaches this x): lets K2 compare boxcar SUMS and divide only what leaves the kernel.
+static float least_sum_reaching(float level, int divisor) {
+  if (!std::isfinite(level)) return level;
+  const float d = static_cast<float>(divisor);
+  float x = level * d;
+  for (int i = 0; i < 64 && !(x / d >= level); ++i) x = std::nextafterf(x, INFINITY);
+  for (int i = 0; i < 64 && std::nextafterf(x, -INFINITY) / d >= level; ++i) x = std::nextafterf(x, -INFINITY);
+  return x;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -629,10 +644,9 @@ int b2s_band_reset(b2s_band* b) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(b->stream));
   b->tracker.reset();
-  {
-    std::lock_guard<std::mutex> lk(b->qmutex);
-    b->published_keys.clear();
-  }
+  CU(cudaStreamSynchronize(b->track_stream));
+  CU(cudaMemset(b->d_state.p, 0, sizeof(TrackState)));  // signals.clear(), transmission.cpp:53
+  b->mailbox.clear();
   return b->reset_averager();
 }
 
@@ -716,19 +730,18 @@ int b2s_band_get_transmissions(b2s_band* b, b2s_transmission* out, int cap, int*
 int b2s_band_get_signals(b2s_band* b, int32_t* keys, int64_t* first, int64_t* last, float* power, int cap, int* count) {
   if (!b || !count) return fail(B2S_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lock(b->mutex);
+  CU(cudaSetDevice(b->engine->device));
   int rc = b->drain();
   if (rc) return rc;
-  int i = 0;
-  for (const auto& kv : b->tracker.signals) {
-    if (i < cap) {
-      if (keys) keys[i] = kv.first;
-      if (first) first[i] = kv.second.first;
-      if (last) last[i] = kv.second.last;
-      if (power) power[i] = kv.second.power;
-    }
-    ++i;
+  std::vector<TrackState> h(1);  // the map is device resident (K4)
+  if ((rc = b->download_state(h[0]))) return rc;
+  for (int i = 0; i < h[0].n && i < cap; ++i) {
+    if (keys) keys[i] = h[0].key[i];
+    if (first) first[i] = h[0].first[i];
+    if (last) last[i] = h[0].last[i];
+    if (power) power[i] = h[0].power[i];
   }
-  *count = i;
+  *count = h[0].n;
   return 0;
 }
 

@@ -44,6 +44,13 @@ struct PushSlot {
   DevBuf<unsigned long long> cta_ns, peak_packed;
   CUtensorMap psd_map;  // PSD rows [max_frames][N] as a 2-D tensor, box = [32 frames][128 + 2*halo columns] (K2's tile)
   DevBuf<int> cand_flag;
+  // device tracker (K4): runs of the frames' entries, the last frame's boxcar row, the push's result
+  DevBuf<FrameRuns> runs;
+  DevBuf<float> box_last;
+  DevBuf<TrackResult> d_result;
+  PinBuf<TrackResult> h_result;
+  cudaEvent_t sorted_done = nullptr, tev[2] = {nullptr, nullptr};
+  bool host_track = false;  // this chunk's bookkeeping runs on the host (the caller asked for every frame's list)
   PinBuf<int> h_offsets, h_cand_flag;
   PinBuf<unsigned int> h_watch_max;
   PinBuf<DetectEntry> h_entries;
@@ -68,6 +75,11 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
+    runs.release(); box_last.release(); d_result.release(); h_result.release();
+    if (sorted_done) cudaEventDestroy(sorted_done);
+    for (auto& e : tev) {
+      if (e) cudaEventDestroy(e);
+    }
     h_offsets.release(); h_entries.release(); watch_max.release(); cta_ns.release(); peak_packed.release(); cand_flag.release(); h_cand_flag.release(); h_watch_max.release();
     if (gpu_done) cudaEventDestroy(gpu_done);
     for (auto& e : ev) {
@@ -81,6 +93,8 @@ struct b2s_band : public DeviceQueries {
   b2s_band_config cfg{};
   std::mutex mutex;  // serialises API calls on this band
   cudaStream_t own_stream = nullptr, stream = nullptr, finish_stream = nullptr, copy_stream = nullptr;
+  cudaStream_t track_stream = nullptr;  // K4 of push k runs here, beside K1 of push k+1 on `stream`
+  DevBuf<TrackState> d_state;           // the signal map (device resident; tracker.signals mirrors it only inside a host-tracked push)
   cudaEvent_t copy_done[2] = {nullptr, nullptr}, iq_prev_use[2] = {nullptr, nullptr};
   int iq_slot = 0;
   int max_frames = 0;
@@ -126,8 +140,6 @@ struct b2s_band : public DeviceQueries {
   int worker_rc = 0;
   std::string worker_error;
 
-  std::vector<int> published_keys;  // signal-map keys after the most recently finished chunk (guarded by qmutex)
-
   PushSlot* cur = nullptr;  // slot whose finish half is running (DeviceQueries context)
   cudaStream_t fstream() const { return async_mode ? finish_stream : stream; }
 
@@ -146,6 +158,8 @@ struct b2s_band : public DeviceQueries {
     for (auto& e : iq_prev_use) {
       if (e) cudaEventDestroy(e);
     }
+    d_state.release();
+    if (track_stream) cudaStreamDestroy(track_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (finish_stream) cudaStreamDestroy(finish_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -296,6 +310,7 @@ struct b2s_band : public DeviceQueries {
     center = c.center_hz;
     CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&finish_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&track_stream, cudaStreamNonBlocking));
     stream = own_stream;
     int rc = tables.build(c);
     if (rc) return rc;
@@ -332,7 +347,14 @@ struct b2s_band : public DeviceQueries {
       if ((rc = s.h_watch_max.alloc(static_cast<size_t>(max_frames) * kMaxWatch))) return rc;
       if ((rc = s.h_cand_flag.alloc(max_frames))) return rc;
       CU(cudaEventCreateWithFlags(&s.gpu_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&s.sorted_done, cudaEventDisableTiming));
+      if ((rc = s.runs.alloc(max_frames))) return rc;
+      if ((rc = s.box_last.alloc(n))) return rc;
+      if ((rc = s.d_result.alloc(1))) return rc;
+      if ((rc = s.h_result.alloc(1))) return rc;
     }
+    if ((rc = d_state.alloc(1))) return rc;
+    CU(cudaMemset(d_state.p, 0, sizeof(TrackState)));
     if ((rc = d_sum.alloc(n))) return rc;
     for (auto& r : d_ring) {
       if ((rc = r.alloc(Y * n))) return rc;
@@ -368,6 +390,60 @@ struct b2s_band : public DeviceQueries {
       }
       worker = std::thread([this]() { worker_loop(); });
     }
+    return 0;
+  }
+
+  // ---- the signal map: device resident (K4); mirrored into tracker.signals around a host-tracked push ----
+  TrackParams track_params() const {
+    TrackParams tp{};
+    const TrackerParams& p = tracker.p;
+    tp.n = p.n;
+    tp.sample_rate = p.sample_rate;
+    tp.center = center;
+    tp.range_lo = p.range_lo;
+    tp.range_hi = p.range_hi;
+    tp.n_ignored = p.n_ignored;
+    for (int i = 0; i < p.n_ignored; ++i) {
+      tp.ignored_lo[i] = p.ignored_lo[i];
+      tp.ignored_hi[i] = p.ignored_hi[i];
+    }
+    tp.group_size = p.group_size;
+    tp.group_y = p.group_y;
+    tp.start_level = p.start_level;
+    tp.stop_level = p.stop_level;
+    tp.tuning_step = p.tuning_step;
+    tp.min_time = p.min_time;
+    tp.timeout = p.timeout;
+    tp.max_time = p.max_time;
+    return tp;
+  }
+  int download_state(TrackState& h) {
+    CU(cudaStreamSynchronize(track_stream));
+    CU(cudaMemcpy(&h, d_state.p, sizeof(TrackState), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  int state_to_host_tracker() {
+    std::vector<TrackState> h(1);
+    int rc = download_state(h[0]);
+    if (rc) return rc;
+    tracker.signals.clear();
+    for (int i = 0; i < h[0].n; ++i) tracker.signals[h[0].key[i]] = TrackedSignal{h[0].first[i], h[0].last[i], h[0].power[i], -1};
+    return 0;
+  }
+  int host_tracker_to_state() {
+    if (tracker.signals.size() > static_cast<size_t>(kMaxSignals)) return fail(B2S_E_OVERFLOW, "%zu live signals; the engine tracks at most %d per band", tracker.signals.size(), kMaxSignals);
+    std::vector<TrackState> h(1);
+    std::memset(&h[0], 0, sizeof(TrackState));
+    int i = 0;
+    for (const auto& kv : tracker.signals) {
+      h[0].key[i] = kv.first;
+      h[0].first[i] = kv.second.first;
+      h[0].last[i] = kv.second.last;
+      h[0].power[i] = kv.second.power;
+      ++i;
+    }
+    h[0].n = i;
+    CU(cudaMemcpy(d_state.p, &h[0], sizeof(TrackState), cudaMemcpyHostToDevice));
     return 0;
   }
 
@@ -511,6 +587,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   const int T = static_cast<int>(frames);
   const size_t bytes_per_sample = cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
   int rc;
+  s.host_track = out && out->frame_tx_count;  // every frame's list is wanted: the bookkeeping runs on the host (tracker.h)
+  if (s.host_track && (rc = state_to_host_tracker())) return rc;
   s.dense_q_on = out && out->noise_sub_db;
   s.dense_avg_on = out && out->avg_db;
   s.dense_box_on = out && out->box_db;
@@ -577,10 +655,11 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
   CU(cudaMemsetAsync(s.max_count.p, 0, sizeof(int), stream));
   CU(cudaMemsetAsync(s.cand_flag.p, 0, sizeof(int) * T, stream));
-  {
-    std::lock_guard<std::mutex> lk(qmutex);
-    s.n_watch = std::min<int>(static_cast<int>(published_keys.size()), kMaxWatch);
-    for (int i = 0; i < s.n_watch; ++i) s.watch_key[i] = published_keys[i];
+  s.n_watch = 0;
+  if (s.host_track) {  // the host tracker is helped by K2's watched-window maxima of the keys that are live now
+    for (const auto& kv : tracker.signals) {
+      if (s.n_watch < kMaxWatch) s.watch_key[s.n_watch++] = kv.first;
+    }
   }
   if (s.n_watch > 0) CU(cudaMemsetAsync(s.watch_max.p, 0, sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch, stream));
   const int ring_in = ring_cur, ring_out = (ring_cur + 1) % kRings;
@@ -600,6 +679,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.avg_last = d_avg_last.p;
   da.checkpoints = s.ckpt.p;
   da.detect_level = std::min(cfg.start_level, cfg.stop_level);
+  da.detect_sum = least_sum_reaching(da.detect_level, cfg.grouping_x);
+  da.start_sum = least_sum_reaching(cfg.start_level, cfg.grouping_x);
   da.slots = d_slots.p;
   da.slot_count = d_slot_count.p;
   da.slot_capacity = slot_capacity;
@@ -617,6 +698,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     da.emit_div[i] = emit_divs[i];
   }
   da.spec_rows = s.spec_rows.p;
+  da.box_last = s.host_track ? nullptr : s.box_last.p;
   da.cta_ns = nullptr;
   if (profiling && profile_ctas) {
     if ((rc = s.cta_ns.alloc(2 * ((n + detect_bins - 1) / detect_bins)))) return rc;
@@ -653,7 +735,47 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     CU(cudaGetLastError());
     if (profiling) CU(cudaEventRecord(s.ev[3], stream));
   }
-  CU(cudaEventRecord(s.gpu_done, stream));
+  if (!s.host_track) {
+    // ---- K4 on its own stream: the signal map advances on the device while `stream` is free for the next push's K1 ----
+    CU(cudaEventRecord(s.sorted_done, stream));
+    CU(cudaStreamWaitEvent(track_stream, s.sorted_done, 0));
+    TrackArgs ta{};
+    ta.p = track_params();
+    ta.n_frames = T;
+    ta.t0_ms = t0_ms;
+    ta.period_ms = period_ms;
+    ta.frame_offset = static_cast<long long>(frame_offset);
+    ta.entries = s.sorted.p;
+    ta.offsets = s.offsets.p;
+    ta.max_count = s.max_count.p;
+    ta.runs = s.runs.p;
+    ta.box_last = s.box_last.p;
+    ta.psd = s.psd.p;
+    ta.threshold = ns->threshold.p;
+    ta.noise_samples = da.noise_samples;
+    ta.learn_frames = cfg.learn_frames;
+    ta.ring_before = d_ring[ring_in].p;
+    ta.state = d_state.p;
+    ta.result = s.d_result.p;
+    if ((rc = prepare_kernel(engine, k_track, kTrackThreads, sizeof(TrackShared), nullptr))) return rc;
+    if (profiling) {
+      for (auto& e : s.tev) {
+        if (!e) CU(cudaEventCreate(&e));
+      }
+      CU(cudaEventRecord(s.tev[0], track_stream));
+    }
+    k_runs<<<(T * 32 + 255) / 256, 256, 0, track_stream>>>(s.sorted.p, s.offsets.p, T, ta.p, s.runs.p);
+    CU(cudaGetLastError());
+    k_track<<<1, kTrackThreads, sizeof(TrackShared), track_stream>>>(ta);
+    CU(cudaGetLastError());
+    if (profiling) CU(cudaEventRecord(s.tev[1], track_stream));
+    // the result header and the first B2S_MAX_TX transmissions (the rest, if any, is fetched by the finish half)
+    CU(cudaMemcpyAsync(s.h_result.p, s.d_result.p, offsetof(TrackResult, tx) + sizeof(b2s_transmission) * B2S_MAX_TX, cudaMemcpyDeviceToHost, track_stream));
+    CU(cudaEventRecord(s.gpu_done, track_stream));
+    prof.track_launches += 1;
+  } else {
+    CU(cudaEventRecord(s.gpu_done, stream));
+  }
 
   // context for the finish half
   s.T = T;
@@ -681,23 +803,81 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   return 0;
 }
 
-// Result half: blocks on the slot's GPU work, then runs the host bookkeeping. Uses fstream() for its own transfers.
+// Result half: blocks on the slot's GPU work, then collects the results. Uses fstream() for its own transfers.
+// Device-tracked chunks (the normal case) only read K4's result back; host-tracked chunks (the caller wants every frame's
+// list) read the detection entries back and run tracker.h.
 int b2s_band::finish_chunk(PushSlot& s) {
   cur = &s;
   cudaStream_t st = fstream();
   const int n = cfg.fft_size, T = s.T, M = cfg.spectrogram_out_size;
   int rc;
   b2s_result* out = s.out;
-  if (st != stream) CU(cudaStreamWaitEvent(st, s.gpu_done, 0));
-  int* h_off = s.h_offsets.p;
-  int* h_max = s.h_offsets.p + max_frames + 1;
-  CU(cudaMemcpyAsync(h_off, s.offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_max, s.max_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(s.h_cand_flag.p, s.cand_flag.p, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
-  if (s.n_watch > 0) CU(cudaMemcpyAsync(s.h_watch_max.p, s.watch_max.p, sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  const int n_entries = h_off[T];
-  prof.d2h_bytes += sizeof(int) * (2 * T + 2) + (s.n_watch > 0 ? sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch : 0);
+  int n_entries = 0;
+  bool overflow = false;
+  int worst_count = 0;
+  if (!s.host_track) {
+    CU(cudaEventSynchronize(s.gpu_done));  // K1, K2, ordering, K4 and the result copy
+    if (st != stream) CU(cudaStreamWaitEvent(st, s.gpu_done, 0));
+    const auto host_t0 = std::chrono::steady_clock::now();
+    const TrackResult& r = *s.h_result.p;
+    prof.d2h_bytes += offsetof(TrackResult, tx) + sizeof(b2s_transmission) * B2S_MAX_TX;
+    if (r.error & 1) return fail(B2S_E_OVERFLOW, "more than %d live signals in one band", kMaxSignals);
+    if (r.error & 2) return fail(B2S_E_OVERFLOW, "more than %d start-level candidates in one frame", kMaxCand);
+    n_entries = r.n_entries;
+    worst_count = r.max_count;
+    overflow = worst_count > slot_capacity;
+    mailbox.resize(r.n_tx);
+    std::memcpy(mailbox.data(), r.tx, sizeof(b2s_transmission) * std::min(r.n_tx, B2S_MAX_TX));
+    if (r.n_tx > B2S_MAX_TX) {  // rare: the tail of a long list
+      CU(cudaMemcpyAsync(mailbox.data() + B2S_MAX_TX, s.d_result.p->tx + B2S_MAX_TX, sizeof(b2s_transmission) * (r.n_tx - B2S_MAX_TX), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      prof.d2h_bytes += sizeof(b2s_transmission) * (r.n_tx - B2S_MAX_TX);
+    }
+    if (profiling && s.tev[0]) {
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, s.tev[0], s.tev[1]));
+      prof.track_ms += ms;
+    }
+    prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  } else {
+    if (st != stream) CU(cudaStreamWaitEvent(st, s.gpu_done, 0));
+    int* h_off = s.h_offsets.p;
+    int* h_max = s.h_offsets.p + max_frames + 1;
+    CU(cudaMemcpyAsync(h_off, s.offsets.p, sizeof(int) * (T + 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_max, s.max_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.h_cand_flag.p, s.cand_flag.p, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
+    if (s.n_watch > 0) CU(cudaMemcpyAsync(s.h_watch_max.p, s.watch_max.p, sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_entries = h_off[T];
+    prof.d2h_bytes += sizeof(int) * (2 * T + 2) + (s.n_watch > 0 ? sizeof(unsigned int) * static_cast<size_t>(T) * kMaxWatch : 0);
+    const auto host_t0 = std::chrono::steady_clock::now();
+    worst_count = *h_max;
+    overflow = worst_count > slot_capacity;  // the push completes on the truncated lists (device and host state stay in step); reported below
+    if (n_entries > 0) {
+      if ((rc = s.h_entries.alloc(n_entries))) return rc;
+      CU(cudaMemcpyAsync(s.h_entries.p, s.sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
+    }
+    std::vector<Tracker::FrameState> states;
+    tracker.p.center = s.center;
+    Tracker::Watch watch{s.n_watch, s.watch_key, s.h_watch_max.p, s.h_cand_flag.p};
+    rc = tracker.run(s.h_entries.p, h_off, T, s.t0_ms, s.period_ms, s.frame_offset, *this, true, watch, states);
+    if (rc) return rc;
+    prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    // the mailbox after the last frame of this chunk (Notification::notify, transmission.cpp:67)
+    mailbox.clear();
+    if (!states.empty() && states.back().frame == T - 1) {
+      mailbox.resize(states.back().keys.size());
+      tracker.sorted_transmissions(states.back(), mailbox.data(), static_cast<int>(mailbox.size()));
+    }
+    for (int t = 0; t < T; ++t) out->frame_tx_count[s.frame_offset + t] = 0;
+    for (const auto& fs : states) {
+      out->frame_tx_count[s.frame_offset + fs.frame] =
+          tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (s.frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
+    }
+    if ((rc = host_tracker_to_state())) return rc;  // the device copy of the map follows the host's
+  }
   if (profiling && s.ev[0]) {
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
@@ -716,46 +896,12 @@ int b2s_band::finish_chunk(PushSlot& s) {
       prof.detect_cta_max_ms += dur[grid - 1];
     }
   }
-  const auto host_t0 = std::chrono::steady_clock::now();
-  const bool overflow = *h_max > slot_capacity;  // the push completes on the truncated lists (device and host state stay in step); reported below
-  if (overflow) wanted_capacity = std::max(wanted_capacity, 2 * *h_max);
-  if (n_entries > 0) {
-    if ((rc = s.h_entries.alloc(n_entries))) return rc;
-    CU(cudaMemcpyAsync(s.h_entries.p, s.sorted.p, sizeof(DetectEntry) * n_entries, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    prof.d2h_bytes += sizeof(DetectEntry) * n_entries;
-  }
-  const bool every = out && out->frame_tx_count;
-  std::vector<Tracker::FrameState> states;
-  tracker.p.center = s.center;
-  Tracker::Watch watch{s.n_watch, s.watch_key, s.h_watch_max.p, s.h_cand_flag.p};
-  rc = tracker.run(s.h_entries.p, h_off, T, s.t0_ms, s.period_ms, s.frame_offset, *this, every, watch, states);
-  if (rc) return rc;
-  {
-    std::lock_guard<std::mutex> lk(qmutex);
-    published_keys.clear();
-    for (const auto& kv : tracker.signals) published_keys.push_back(kv.first);
-  }
-  prof.tracker_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-
-  // the mailbox after the last frame of this chunk (Notification::notify, transmission.cpp:67)
-  mailbox.clear();
-  if (!states.empty() && states.back().frame == T - 1) {
-    mailbox.resize(states.back().keys.size());
-    tracker.sorted_transmissions(states.back(), mailbox.data(), static_cast<int>(mailbox.size()));
-  }
+  if (overflow) wanted_capacity = std::max(wanted_capacity, 2 * worst_count);
   stat_entries += n_entries;
   stat_rows += s.n_emit;
   if (out) {
     out->n_detect_entries += n_entries;
     out->n_spectrogram_rows += s.n_emit;
-    if (every) {
-      for (int t = 0; t < T; ++t) out->frame_tx_count[s.frame_offset + t] = 0;
-      for (const auto& fs : states) {
-        out->frame_tx_count[s.frame_offset + fs.frame] =
-            tracker.sorted_transmissions(fs, out->frame_tx ? out->frame_tx + (s.frame_offset + fs.frame) * B2S_MAX_TX : nullptr, out->frame_tx ? B2S_MAX_TX : 0);
-      }
-    }
     out->n_transmissions_total = static_cast<int32_t>(mailbox.size());
     out->n_transmissions = std::min<int32_t>(out->n_transmissions_total, B2S_MAX_TX);
     std::memcpy(out->transmissions, mailbox.data(), sizeof(b2s_transmission) * out->n_transmissions);
@@ -779,6 +925,6 @@ int b2s_band::finish_chunk(PushSlot& s) {
   cur = nullptr;
   if (overflow)
     return fail(B2S_E_OVERFLOW, "a frame produced %d detection entries but detect_capacity is %d per frame: the frame's list was truncated (the push completed on the "
-                "truncated lists); the capacity grows to %d before the next push", *h_max, slot_capacity, std::min(cfg.fft_size, wanted_capacity));
+                "truncated lists); the capacity grows to %d before the next push", worst_count, slot_capacity, std::min(cfg.fft_size, wanted_capacity));
   return 0;
 }

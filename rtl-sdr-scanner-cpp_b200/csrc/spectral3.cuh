@@ -109,10 +109,12 @@ constexpr int kSplitStageBytes = 32768; // one staging buffer: S row segments of
 // and X[S k' + c] = FFT_16384(y_c)[k'] with exactly the passes of the non-split kernel. The S items of one frame are
 // adjacent in the work order: they read the same int8 frame (L2 hits after the first) and fill the same output sectors.
 // The int8 frame reaches the pre-pass through a 2-stage ring of bulk copies (S row segments per stage).
-template <int RA, int MODE, bool DEBUG_LIN, bool SPLIT>
+template <int RA, int MODE, bool DEBUG_LIN, int SPLIT_S>
 __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
+  constexpr bool SPLIT = SPLIT_S > 1;
   constexpr int M = RA * 1024, T = RA * 32, BPT = 32 / RA;  // sub-transform length, threads, pass-A butterflies per thread
   static_assert(!SPLIT || RA == 16, "the split mode runs 16384-point sub-transforms");
+  static_assert(SPLIT_S == 1 || SPLIT_S == 2 || SPLIT_S == 4 || SPLIT_S == 8 || SPLIT_S == 16, "S");
   extern __shared__ __align__(128) unsigned char smem[];
   float2* X = reinterpret_cast<float2*>(smem);                                 // [RA][kBlockPitch]
   float2* twB = X + RA * kBlockPitch;                                          // [31][32]
@@ -127,10 +129,10 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const char* base = static_cast<const char*>(a.iq);
   const float2* twA = a.twiddle;
-  const int S = SPLIT ? a.split : 1;
-  const int N = S * M;
+  constexpr int S = SPLIT_S;
+  constexpr int N = S * M;
   const int n_items = a.n_frames * S;
-  const int pc = SPLIT ? M / S : M;  // samples per row segment of a stage
+  constexpr int pc = M / S;  // samples per row segment of a stage
 
   if (MODE == kModeCs8Tma && tid == 0) {
     mbar_init(&full_bar[0], 1);
@@ -174,9 +176,12 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
       for (int q = 0; q < S; ++q) {
         const unsigned char* st = raw + (chunk_no & 1u) * kSplitStageBytes;
         if (MODE == kModeCs8Tma) mbar_wait(&full_bar[chunk_no & 1u], (chunk_no >> 1) & 1u);
-        for (int i = tid; i < pc; i += T) {
+#pragma unroll(S >= 8 ? 2 : 4)
+        for (int u = 0; u < pc / T; ++u) {  // independent points: their loads overlap
+          const int i = tid + u * T;
           const int np = q * pc + i;
           float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
           for (int s = 0; s < S; ++s) {
             const int n = np + s * M;
             const float w = __ldg(&a.wscale[n]);

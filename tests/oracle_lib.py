@@ -359,8 +359,15 @@ def db_rows_stats(got_db, ref_db):
     }
 
 
+def worst_tolerance(n_fft):
+    """Bound on the single worst floored relative power error of a row. 1e-4 up to N = 16384; above, it widens with sqrt(N / 16384):
+    the worst of N samples of fp32 rounding noise grows with N and log N — the oracle's OWN fp32 FFT against its fp64 FFT gives
+    3.0e-5 / 6.1e-5 / 9.1e-5 for one frame of N = 16384 / 65536 / 262144 (measured)."""
+    return 1e-4 * max(1.0, n_fft / 16384.0) ** 0.5
+
+
 def assert_db_rows_close(got_db, ref_db, what=""):
     st = db_rows_stats(got_db, ref_db)
     # 1e-5 relative on power == 4.3e-5 dB; the fp32 rounding of a dB value near -70 is already 3.8e-6 dB
-    assert st["worst"] <= 1e-4 and st["pass_frac"] >= 0.995 and st["db_max_main"] <= 2e-3, (what, st)
+    assert st["worst"] <= worst_tolerance(np.asarray(ref_db).shape[-1]) and st["pass_frac"] >= 0.995 and st["db_max_main"] <= 2e-3, (what, st)
     return st

@@ -49,7 +49,7 @@ def test_psd_rows_match_oracle(engine, n):
     ol.assert_db_rows_close(psd, ref, f"N={n}")
     st = power_parity_stats(lin, ref_lin)
     print(f"\nN={n}: floored pass {st['pass_frac']:.5f} worst {st['worst']:.2e} strict pass {st['strict_frac']:.4f} L2rel {st['l2_rel']:.2e}")
-    assert st["pass_frac"] >= 0.995 and st["worst"] <= 1e-4 and st["l2_rel"] <= 1e-6, st
+    assert st["pass_frac"] >= 0.995 and st["worst"] <= ol.worst_tolerance(n) and st["l2_rel"] <= 1e-6, st
     assert np.array_equal(np.argmax(psd, axis=1), np.argmax(ref, axis=1))
 
 
@@ -562,11 +562,45 @@ def test_exact_constant_division_exhaustive(engine):
         assert bad == 0, (d, bad)
 
 
-def test_more_signals_than_the_result_struct_holds(engine):
-    """The signal map is not limited to B2S_MAX_TX (the reference's std::map is unbounded): 80 simultaneous carriers are all
-    tracked; the embedded array holds the 64 strongest and says so, b2s_band_get_transmissions returns the whole list."""
+@pytest.mark.parametrize("n,fs,frames,learn", [(1024, 1_024_000, 700, 40), (4096, 4_096_000, 420, 30)])
+def test_device_tracker_mailbox_after_every_push(engine, n, fs, frames, learn):
+    """K4 (the signal map on the device, csrc/track.cuh) against the oracle: the scene is pushed in pieces of 1..97 frames, many of
+    them single frames, so the mailbox after each push is the oracle's list of that frame — starts, flushes, stops and time-outs
+    included. Every fifth push asks for per-frame lists instead, which hands the map to the host tracker and back."""
+    cfg, tones, iq, period = scene(n, fs, frames, learn)
+    assert period == 1.0  # the frame clock is additive at any split point
+    o = ol.OracleChain(cfg)
+    ref = o.push(iq, frames, 500, period, dense=())
+    band = b2s.Band(engine, cfg)
+    sizes, k, i, checked = [1, 1, 1, 2, 5, 1, 20, 21, 1, 22, 97, 3, 1, 60, 1, 1, 80, 33, 1, 7], 0, 0, 0
+    while k < frames:
+        m = min(sizes[i % len(sizes)], frames - k)
+        if i % 5 == 4:
+            r = band.push(iq[k * 2 * n :], m, 500 + k, period, per_frame=True)
+            assert _tx(r.frame_tx) == _tx(ref.frame_tx[k : k + m]), (k, m)
+            got = r.transmissions
+        else:
+            res = band.push_raw(iq[k * 2 * n :].ctypes.data, m, 500 + k, period)
+            got = [(t.shift_hz, t.flush, t.key, t.power) for t in res.transmissions[: res.n_transmissions]]
+        want = ref.frame_tx[k + m - 1]
+        assert [(f, fl, key) for f, fl, key, _ in got] == [(f, fl, key) for f, fl, key, _ in want], (k, m, got, want)
+        for (_, _, _, pa), (_, _, _, pb) in zip(got, want):
+            assert abs(pa - pb) <= 4e-3
+        checked += len(want)
+        i += 1
+        k += m
+    assert checked > 100
+    for a, b in zip(band.get_signals()[:3], o.get_signals()[:3]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("count,spacing", [(80, 97), (150, 52)])
+def test_more_signals_than_the_result_struct_holds(engine, count, spacing):
+    """The signal map is not limited to B2S_MAX_TX (the reference's std::map is unbounded): 80 / 150 simultaneous carriers are all
+    tracked (150 exceeds the key chunk K4 holds in shared memory at a time); the embedded array holds the 64 strongest and says
+    so, b2s_band_get_transmissions returns the whole list."""
     n, fs, frames, learn = 8192, 8_192_000, 80, 20
-    tones = [synth.Tone(-3900.1 + 97 * i, amplitude=30.0 + (i % 7), fm_dev_bins=3.0) for i in range(80)]
+    tones = [synth.Tone(-3900.1 + spacing * i, amplitude=30.0 + (i % 7), fm_dev_bins=3.0) for i in range(count)]
     iq = synth.make_iq_int8(n, frames, tones, seed=9, quiet_frames=learn)
     cfg = b2s.make_config(n, fs, learn_frames=learn, group_size_bins=16, min_time_ms=10, timeout_ms=30)
     band = b2s.Band(engine, cfg)
@@ -575,7 +609,7 @@ def test_more_signals_than_the_result_struct_holds(engine):
     o = ol.OracleChain(cfg)
     o.push(iq, frames, 0, period, dense=())
     want = [(f, fl, k) for f, fl, k, _ in o.get_transmissions()]
-    assert len(want) >= 70
+    assert len(want) >= count - 10
     assert res.n_transmissions_total == len(want) and res.n_transmissions == b2s.MAX_TX
     assert [(f, fl, k) for f, fl, k, _ in band.get_transmissions()] == want
     assert _mailbox(res) == want[: b2s.MAX_TX]
