@@ -97,6 +97,9 @@ class Profile(C.Structure):
         ("detect_cta_max_ms", C.c_double),
         ("track_ms", C.c_double),
         ("track_launches", C.c_int64),
+        ("track_evals", C.c_int64),
+        ("track_events", C.c_int64),
+        ("track_best_index", C.c_int64),
     ]
 
 

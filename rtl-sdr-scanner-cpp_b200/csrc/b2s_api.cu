@@ -161,7 +161,7 @@ int launch_spectrum3_v(b2s_engine* e, const SpectralArgs& a, cudaStream_t stream
   if (!a.work_counter) return fail(B2S_E_INVALID, "k_spectrum3 needs a work counter");
   const int items = a.n_frames * S;
   if (a.split != S) return fail(B2S_E_INVALID, "split tables were built for another fft_size");
-  const int grid = std::min(items, e->sm_count * ctas_per_sm);
+  const int grid = std::min(items, std::max(1, e->sm_count - a.reserve_sms) * ctas_per_sm);
   if (SPLIT) {
     if (!a.peak_packed || !a.split_tw || !a.split_ws) return fail(B2S_E_INVALID, "split-mode tables are missing");
     CU(cudaMemsetAsync(a.peak_packed, 0, sizeof(unsigned long long) * a.n_frames, stream));

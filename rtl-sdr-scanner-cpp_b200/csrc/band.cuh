@@ -45,7 +45,6 @@ struct PushSlot {
   CUtensorMap psd_map;  // PSD rows [max_frames][N] as a 2-D tensor, box = [32 frames][128 + 2*halo columns] (K2's tile)
   DevBuf<int> cand_flag;
   // device tracker (K4): runs of the frames' entries, the last frame's boxcar row, the push's result
-  DevBuf<FrameRuns> runs;
   DevBuf<float> box_last;
   DevBuf<TrackResult> d_result;
   PinBuf<TrackResult> h_result;
@@ -75,7 +74,7 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
-    runs.release(); box_last.release(); d_result.release(); h_result.release();
+    box_last.release(); d_result.release(); h_result.release();
     if (sorted_done) cudaEventDestroy(sorted_done);
     for (auto& e : tev) {
       if (e) cudaEventDestroy(e);
@@ -317,14 +316,24 @@ struct b2s_band : public DeviceQueries {
     cfg.window_taps = nullptr;
     const size_t n = c.fft_size, Y = c.grouping_y;
     const int n_slots = async_mode ? kPushSlots : 1;
-    // K2's CTA width: 112 bins put N = 16384 on 147 SMs (128 would use 128 of the 148); a spectrogram column of d raw bins must not
-    // straddle two CTAs, and the halo has to fit the SUM warps' columns
+    // K2's CTA width: 112 bins put N = 16384 on 147 SMs (128 would use 128 of the 148). A spectrogram column of d raw bins must not
+    // straddle two CTAs, and the bins plus both boxcar halos have to fit the SUM warps' columns.
     {
       const int d = c.spectrogram_out_size > 0 ? c.fft_size / c.spectrogram_out_size : 1;
       const int hp = (c.grouping_x / 2 + 3) & ~3;
-      detect_bins = (112 % d == 0 && 112 + 2 * hp <= kSumThreads) ? 112 : kDetectBinsPerCta;
-      if (const char* e = getenv("B2S_K2_BINS")) detect_bins = atoi(e) == 112 && 112 % d == 0 ? 112 : kDetectBinsPerCta;  // A/B measurements
-      if (detect_bins + 2 * hp > kSumThreads) return fail(B2S_E_INVALID, "grouping_x %d needs a halo of %d bins per side; one K2 CTA holds at most %d columns", c.grouping_x, hp, kSumThreads);
+      detect_bins = 0;
+      for (int bins : {112, 128, 96, 64}) {
+        if (bins % d == 0 && bins + 2 * hp <= kSumThreads) {
+          detect_bins = bins;
+          break;
+        }
+      }
+      if (const char* e = getenv("B2S_K2_BINS")) {  // A/B measurements
+        const int bins = atoi(e);
+        if (bins > 0 && bins <= kDetectBinsPerCta && bins % kBoxSegment == 0 && bins % d == 0 && bins + 2 * hp <= kSumThreads) detect_bins = bins;
+      }
+      if (!detect_bins)
+        return fail(B2S_E_INVALID, "grouping_x %d (halo %d bins per side) with a spectrogram decimation of %d does not fit a K2 CTA of %d columns", c.grouping_x, hp, d, kSumThreads);
     }
     for (int i = 0; i < n_slots; ++i) {
       PushSlot& s = slots[i];
@@ -348,7 +357,6 @@ struct b2s_band : public DeviceQueries {
       if ((rc = s.h_cand_flag.alloc(max_frames))) return rc;
       CU(cudaEventCreateWithFlags(&s.gpu_done, cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&s.sorted_done, cudaEventDisableTiming));
-      if ((rc = s.runs.alloc(max_frames))) return rc;
       if ((rc = s.box_last.alloc(n))) return rc;
       if ((rc = s.d_result.alloc(1))) return rc;
       if ((rc = s.h_result.alloc(1))) return rc;
@@ -394,19 +402,32 @@ struct b2s_band : public DeviceQueries {
   }
 
   // ---- the signal map: device resident (K4); mirrored into tracker.signals around a host-tracked push ----
-  TrackParams track_params() const {
+  // bins whose frequency (indexToFrequency, sdr_device.cpp:153) lies in [f_lo, f_hi]: the frequency is monotonic in the bin
+  void bins_between(int32_t f_lo, int32_t f_hi, int* lo, int* hi) const {
+    const int n = tracker.p.n;
+    int a = 0, b = n;  // first bin with frequency >= f_lo
+    while (a < b) {
+      const int m = (a + b) / 2;
+      if (tracker.index_to_frequency(m) < f_lo) a = m + 1; else b = m;
+    }
+    *lo = a;
+    a = 0, b = n;      // first bin with frequency > f_hi
+    while (a < b) {
+      const int m = (a + b) / 2;
+      if (tracker.index_to_frequency(m) <= f_hi) a = m + 1; else b = m;
+    }
+    *hi = a - 1;
+  }
+  TrackParams track_params() {
     TrackParams tp{};
+    tracker.p.center = center;
     const TrackerParams& p = tracker.p;
     tp.n = p.n;
     tp.sample_rate = p.sample_rate;
     tp.center = center;
-    tp.range_lo = p.range_lo;
-    tp.range_hi = p.range_hi;
+    bins_between(p.range_lo, p.range_hi, &tp.bin_lo, &tp.bin_hi);
     tp.n_ignored = p.n_ignored;
-    for (int i = 0; i < p.n_ignored; ++i) {
-      tp.ignored_lo[i] = p.ignored_lo[i];
-      tp.ignored_hi[i] = p.ignored_hi[i];
-    }
+    for (int i = 0; i < p.n_ignored; ++i) bins_between(p.ignored_lo[i], p.ignored_hi[i], &tp.ignored_lo[i], &tp.ignored_hi[i]);
     tp.group_size = p.group_size;
     tp.group_y = p.group_y;
     tp.start_level = p.start_level;
@@ -608,6 +629,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   sa.n_frames = T;
   tables.fill(sa);
   sa.peak_packed = s.peak_packed.p;
+  sa.reserve_sms = 1;  // K4 (one CTA, on track_stream) runs beside this K1: the persistent grid leaves it an SM
   sa.inv_fs = 1.0f / static_cast<float>(cfg.sample_rate_hz);
   sa.psd_db = s.psd.p;
   sa.power_lin = nullptr;
@@ -748,7 +770,6 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     ta.entries = s.sorted.p;
     ta.offsets = s.offsets.p;
     ta.max_count = s.max_count.p;
-    ta.runs = s.runs.p;
     ta.box_last = s.box_last.p;
     ta.psd = s.psd.p;
     ta.threshold = ns->threshold.p;
@@ -757,6 +778,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     ta.ring_before = d_ring[ring_in].p;
     ta.state = d_state.p;
     ta.result = s.d_result.p;
+    if (const char* e = getenv("B2S_TRACK_DEBUG")) ta.debug = atoi(e) >= 2;
     if ((rc = prepare_kernel(engine, k_track, kTrackThreads, sizeof(TrackShared), nullptr))) return rc;
     if (profiling) {
       for (auto& e : s.tev) {
@@ -764,8 +786,6 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
       }
       CU(cudaEventRecord(s.tev[0], track_stream));
     }
-    k_runs<<<(T * 32 + 255) / 256, 256, 0, track_stream>>>(s.sorted.p, s.offsets.p, T, ta.p, s.runs.p);
-    CU(cudaGetLastError());
     k_track<<<1, kTrackThreads, sizeof(TrackShared), track_stream>>>(ta);
     CU(cudaGetLastError());
     if (profiling) CU(cudaEventRecord(s.tev[1], track_stream));
@@ -825,6 +845,12 @@ int b2s_band::finish_chunk(PushSlot& s) {
     if (r.error & 2) return fail(B2S_E_OVERFLOW, "more than %d start-level candidates in one frame", kMaxCand);
     n_entries = r.n_entries;
     worst_count = r.max_count;
+    prof.track_evals += r.n_evals;
+    prof.track_events += r.n_events;
+    prof.track_best_index += r.n_best;
+    if (getenv("B2S_TRACK_DEBUG"))
+      fprintf(stderr, "[k_track] T=%d cycles %lld: runs %lld eval %lld walk %lld out %lld; evals %d events %d best %d entries %d\n", T, r.cycles, r.phase[0], r.phase[1], r.phase[2],
+              r.phase[3], r.n_evals, r.n_events, r.n_best, r.n_entries);
     overflow = worst_count > slot_capacity;
     mailbox.resize(r.n_tx);
     std::memcpy(mailbox.data(), r.tx, sizeof(b2s_transmission) * std::min(r.n_tx, B2S_MAX_TX));

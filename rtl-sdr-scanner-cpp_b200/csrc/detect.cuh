@@ -202,8 +202,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 #define B2S_K2_BOX_GROUPS 2
 #endif
 constexpr int kBoxGroups = B2S_K2_BOX_GROUPS;  // box-warp groups; group g takes the tiles with (tile % kBoxGroups) == g (1 or 2)
-constexpr int kSumWarps = 6, kBoxWarps = kDetectBinsPerCta / kBoxSegment;
-constexpr int kSumThreads = 32 * kSumWarps;    // one thread per column (<= 192 columns)
+constexpr int kSumWarps = 5, kBoxWarps = kDetectBinsPerCta / kBoxSegment;
+constexpr int kSumThreads = 32 * kSumWarps;    // one thread per column (<= 160 columns: the CTA's bins plus both halos)
 constexpr int kBoxThreads = 32 * kBoxWarps;    // threads of ONE box group: one warp per boxcar segment, lane = frame of the tile
 constexpr int kSpecWarps = 2;                  // decimating spectrograms (N / out = d > 1): thread = spectrogram column, kDetectBinsPerCta / 2 at most
 constexpr int kSpecThreads = 32 * kSpecWarps;
@@ -219,7 +219,8 @@ constexpr int kSumBase = B2S_K2_SUM_LAST ? kBoxGroups * kBoxThreads + 32 + kSpec
 constexpr int kSpecBase = B2S_K2_SUM_LAST ? kBoxGroups * kBoxThreads + 32 : kSumThreads + 32 + kBoxGroups * kBoxThreads;
 // registers per thread: the hardware allocates per warp in units of 512, so 23 warps get at most 2560 = 32 x 80
 constexpr int kDetectRegs = 80;
-static_assert((kDetectThreads / 32) * ((kDetectRegs * 32 + 511) / 512 * 512) <= 65536, "k_detect must fit the register file");
+// the register file is split over the 4 SM sub-partitions (16384 registers each) and a CTA's warps are dealt round robin
+static_assert(((kDetectThreads / 32 + 3) / 4) * ((kDetectRegs * 32 + 511) / 512 * 512) <= 16384, "k_detect must fit the register file");
 static_assert(kDetectBinsPerCta / 2 <= kSpecThreads, "one SPEC thread per spectrogram column of a CTA");
 #ifndef B2S_K2_AVG_BUFFERS
 #define B2S_K2_AVG_BUFFERS 2

@@ -163,6 +163,7 @@ struct SpectralArgs {
   float* peak_value;            // [n_frames]
   // ---- k_spectrum3 only ----
   int* work_counter;            // [2] {next work item, CTAs finished}: dynamic work distribution; both zero between launches
+  int reserve_sms;              // SMs the persistent grid leaves free (for the band's K4, which runs beside the next push's K1)
   // split mode, N = S * 16384 (S = 2..16): CTA-items (frame, c) each produce the bins k = S k' + c of one frame
   int split;                    // S (1 = off)
   const float2* split_tw;       // [S][16384]  W_N^(n' c)

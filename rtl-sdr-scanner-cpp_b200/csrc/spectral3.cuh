@@ -196,9 +196,17 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
               const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
               xs = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
             }
-            const float2 ws = s_ws[s];
-            acc.x = fmaf(xs.x, ws.x, fmaf(-xs.y, ws.y, acc.x));
-            acc.y = fmaf(xs.x, ws.y, fmaf(xs.y, ws.x, acc.y));
+            if (s == 0) {  // W_S^0 = 1
+              acc = xs;
+            } else if (S == 2) {  // W_2^c = +-1
+              const float sign = c ? -1.0f : 1.0f;
+              acc.x = fmaf(sign, xs.x, acc.x);
+              acc.y = fmaf(sign, xs.y, acc.y);
+            } else {
+              const float2 ws = s_ws[s];
+              acc.x = fmaf(xs.x, ws.x, fmaf(-xs.y, ws.y, acc.x));
+              acc.y = fmaf(xs.x, ws.y, fmaf(xs.y, ws.x, acc.y));
+            }
           }
           if (c != 0) acc = cmul(acc, __ldg(&twc[np]));
           X[(np >> 10) * kBlockPitch + (np & 1023)] = acc;
@@ -284,46 +292,49 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     for (int w = 1; w < RA; ++w) row_max = fmaxf(row_max, red_v[w]);
     float* row = a.psd_db + static_cast<size_t>(frame) * N;
     int best_i = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < M / (4 * T); ++i) {
-      const int bin = 4 * (tid + i * T);
-      const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
-      const int k0 = bin & (RA - 1);
-      float4 o;
-      const float* src = Xf + k2 * 32 + k1;
-      o.x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
-      o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
-      o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
-      o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
-      const int jl = (bin + M / 2) & (M - 1);  // local fftshift; the S classes interleave: global bin = S * local + c
-      if (DEBUG_LIN) {  // debug instantiation: the block holds |X|^2/fs; dB is recomputed here
-        float* lin = a.power_lin + static_cast<size_t>(frame) * N;
-        if (SPLIT) {
-          lin[S * jl + c] = o.x;
-          lin[S * (jl + 1) + c] = o.y;
-          lin[S * (jl + 2) + c] = o.z;
-          lin[S * (jl + 3) + c] = o.w;
-        } else {
-          *reinterpret_cast<float4*>(lin + jl) = o;
+    if (SPLIT) {
+      // the S classes of a frame interleave (global bin = S * local + c): consecutive lanes take consecutive local bins, so one warp
+      // store covers 32 * S consecutive floats of the row (every S-th one); the other classes' CTAs fill the rest of the sectors
+      float* lin = DEBUG_LIN ? a.power_lin + static_cast<size_t>(frame) * N : nullptr;
+#pragma unroll 8
+      for (int i = 0; i < M / T; ++i) {
+        const int bin = tid + i * T;
+        const int q = bin / RA, k1 = q & 31, k2 = q >> 5, k0 = bin & (RA - 1);
+        float o = Xf[k0 * (2 * kBlockPitch + 2) + k2 * 32 + k1];  // lanes: 16 blocks x 2 adjacent words -> distinct banks
+        const int j = S * ((bin + M / 2) & (M - 1)) + c;
+        if (DEBUG_LIN) {
+          lin[j] = o;
+          o = kDbPerLog2 * fast_log2(o);
         }
-        o.x = kDbPerLog2 * fast_log2(o.x);
-        o.y = kDbPerLog2 * fast_log2(o.y);
-        o.z = kDbPerLog2 * fast_log2(o.z);
-        o.w = kDbPerLog2 * fast_log2(o.w);
+        row[j] = o;
+        if (o == row_max) best_i = min(best_i, j);
       }
-      if (SPLIT) {
-        row[S * jl + c] = o.x;
-        row[S * (jl + 1) + c] = o.y;
-        row[S * (jl + 2) + c] = o.z;
-        row[S * (jl + 3) + c] = o.w;
-      } else {
-        *reinterpret_cast<float4*>(row + jl) = o;
+    } else {
+#pragma unroll
+      for (int i = 0; i < M / (4 * T); ++i) {
+        const int bin = 4 * (tid + i * T);
+        const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
+        const int k0 = bin & (RA - 1);
+        float4 o;
+        const float* src = Xf + k2 * 32 + k1;
+        o.x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
+        o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
+        o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
+        o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
+        const int j = (bin + M / 2) & (M - 1);
+        if (DEBUG_LIN) {  // debug instantiation: the block holds |X|^2/fs; dB is recomputed here
+          *reinterpret_cast<float4*>(a.power_lin + static_cast<size_t>(frame) * N + j) = o;
+          o.x = kDbPerLog2 * fast_log2(o.x);
+          o.y = kDbPerLog2 * fast_log2(o.y);
+          o.z = kDbPerLog2 * fast_log2(o.z);
+          o.w = kDbPerLog2 * fast_log2(o.w);
+        }
+        *reinterpret_cast<float4*>(row + j) = o;
+        if (o.x == row_max) best_i = min(best_i, j);
+        if (o.y == row_max) best_i = min(best_i, j + 1);
+        if (o.z == row_max) best_i = min(best_i, j + 2);
+        if (o.w == row_max) best_i = min(best_i, j + 3);
       }
-      const int j = SPLIT ? S * jl + c : jl;
-      if (o.x == row_max) best_i = min(best_i, j);
-      if (o.y == row_max) best_i = min(best_i, j + S);
-      if (o.z == row_max) best_i = min(best_i, j + 2 * S);
-      if (o.w == row_max) best_i = min(best_i, j + 3 * S);
     }
     if (best_i != 0x7fffffff) atomicMin(&red_i[0], best_i);
     __syncthreads();  // the exchange buffer is free again; red_i is final

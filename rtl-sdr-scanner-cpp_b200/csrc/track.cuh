@@ -12,8 +12,9 @@
 // whose window [key - g/2, key + g/2] holds a bin at or above the stop level. So the kernel walks the push in blocks of 1024
 // frames, one thread per frame, finds the first event frame of the block in parallel, commits the frames before it in
 // parallel, replays the event frame exactly like the reference (candidates by power, getBestIndex on the Averager ring rows,
-// update, clear) and continues behind it. k_runs first folds each frame's detection entries into runs of consecutive bins
+// update, clear) and continues behind it. Each thread first folds its frame's detection entries into runs of consecutive bins
 // (one per emitter and level), so the per-frame work does not grow with the width of a signal.
+// The kernel is one CTA: K1 leaves one SM free for it (b2s_band keeps it off `stream`), so it runs beside the next push's K1.
 //
 // m_power (only read when the list is emitted) is taken for the last frame of the push from K2's boxcar row of that frame.
 // Tie rules left open by the reference's unstable std::sort are the oracle's: candidates (power desc, bin asc), transmissions
@@ -24,15 +25,19 @@
 
 namespace b2s {
 
-constexpr int kMaxSignals = 1024;  // live signals per band (keys are at least g/2 bins apart); beyond it the push fails loudly
-constexpr int kRunCap = 24;        // runs kept per frame and level; a frame with more is replayed from its raw entries
+constexpr int kMaxSignals = 256;   // live signals per band held by K4; beyond it the push fails loudly (B2S_E_OVERFLOW)
+constexpr int kRunCap = 8;         // runs kept per frame and level; a frame with more is replayed from its raw entries
+constexpr int kRunLenBits = 14;    // a run is packed as (first bin << 14) | (length - 1); longer stretches are cut into several runs
 constexpr int kTrackThreads = 1024, kTrackFrames = 1024, kTrackWords = kTrackFrames / 32;
-constexpr int kKeyChunk = 128;     // keys whose per-frame hit bits are held in shared memory at a time
-constexpr int kMaxCand = 4096;     // candidates of one event frame (= the largest detect_capacity)
+constexpr int kMaxCand = 2048;     // start-level candidates replayed in one event frame
 
 struct TrackParams {  // Transmission's construction-time parameters (transmission.h:17-25) + the index lambdas of sdr_device.cpp:153-158
-  int n, sample_rate, center, range_lo, range_hi;
-  int n_ignored, ignored_lo[B2S_MAX_IGNORED], ignored_hi[B2S_MAX_IGNORED];
+  int n, sample_rate, center;
+  // isIndexInRange / isIndexIgnored (sdr_device.cpp:155-158, transmission.cpp:156-164) as BIN intervals: indexToFrequency is
+  // monotonic in the index, so each frequency interval is one interval of bins; the host finds the bounds with the reference's
+  // own double-precision expression (FP64 is far too slow on this part to evaluate per detection entry)
+  int bin_lo, bin_hi;  // bins whose frequency lies in [range_lo, range_hi]
+  int n_ignored, ignored_lo[B2S_MAX_IGNORED], ignored_hi[B2S_MAX_IGNORED];  // bins (inclusive; lo > hi when empty)
   int group_size, group_y;
   float start_level, stop_level;
   int tuning_step;
@@ -49,12 +54,10 @@ struct TrackState {  // std::map<Index, Signal> (transmission.h:49), keys ascend
 struct TrackResult {  // what the host reads back per push
   int n_tx, n_entries, max_count, error;
   long long last_now;
+  int n_evals, n_events, n_best, pad;  // work counters of the push: block evaluations, event frames replayed, getBestIndex calls
+  long long cycles;                    // SM cycles k_track ran
+  long long phase[4];                  // of which: folding entries into runs, evaluations, event walks (commits + event frames), output
   b2s_transmission tx[kMaxSignals];  // getSortedTransmissions after the last frame
-};
-
-struct FrameRuns {  // runs of consecutive bins of one frame: [0] at or above the stop level, [1] start-level candidates
-  int count[2];     // may exceed kRunCap (then the frame is "complex")
-  int lo[2][kRunCap], hi[2][kRunCap];
 };
 
 struct TrackArgs {
@@ -66,7 +69,6 @@ struct TrackArgs {
   const DetectEntry* entries;  // ordered by (frame, bin)
   const int* offsets;          // [T + 1]
   const int* max_count;        // largest per-frame entry count (overflow report)
-  const FrameRuns* runs;       // [T]
   const float* box_last;       // [N] boxcar row of the last frame
   // getBestIndex inputs: noise-subtracted rows = the Averager ring
   const float* psd;            // [T][N]
@@ -75,6 +77,7 @@ struct TrackArgs {
   const float* ring_before;    // [Y][N] ring before the push, oldest -> newest
   TrackState* state;
   TrackResult* result;
+  int debug;  // printf trace of the evaluations and event frames (B2S_TRACK_DEBUG=2)
 };
 
 __device__ __forceinline__ long long track_frame_time(long long t0, double period, long long k) {
@@ -85,10 +88,9 @@ __device__ __forceinline__ int track_index_to_shift(const TrackParams& p, int i)
   return static_cast<int>(__dmul_rn(step, __dadd_rn(static_cast<double>(i), 0.5))) - p.sample_rate / 2;
 }
 __device__ __forceinline__ bool track_candidate_bin(const TrackParams& p, int i) {  // isIndexInRange && !isIndexIgnored, transmission.cpp:91,156-164
-  const int f = p.center + track_index_to_shift(p, i);
-  if (f < p.range_lo || f > p.range_hi) return false;
+  if (i < p.bin_lo || i > p.bin_hi) return false;
   for (int r = 0; r < p.n_ignored; ++r) {
-    if (p.ignored_lo[r] <= f && f <= p.ignored_hi[r]) return false;
+    if (p.ignored_lo[r] <= i && i <= p.ignored_hi[r]) return false;
   }
   return true;
 }
@@ -115,74 +117,35 @@ __device__ __forceinline__ bool track_within_margin(const int* keys, int n, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_runs: one warp per frame folds the frame's entries (ascending bins) into runs of consecutive bins per level
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_runs(const DetectEntry* entries, const int* offsets, int n_frames, TrackParams p, FrameRuns* runs) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (t >= n_frames) return;
-  const int e0 = offsets[t], e1 = offsets[t + 1];
-  FrameRuns& fr = runs[t];
-  int count[2] = {0, 0};
-  for (int base = e0; base < e1; base += 32) {
-    const int e = base + lane;
-    const bool valid = e < e1;
-    const DetectEntry cur = valid ? entries[e] : DetectEntry{-10, 0.0f};
-    const DetectEntry prev = (valid && e > e0) ? entries[e - 1] : DetectEntry{-10, 0.0f};
-    const DetectEntry next = (valid && e + 1 < e1) ? entries[e + 1] : DetectEntry{-10, 0.0f};
-#pragma unroll
-    for (int L = 0; L < 2; ++L) {
-      auto in = [&](const DetectEntry& d) { return d.bin >= 0 && (L == 0 ? p.stop_level <= d.value : (p.start_level <= d.value && track_candidate_bin(p, d.bin))); };
-      const bool me = valid && in(cur);
-      const bool starts = me && !(prev.bin == cur.bin - 1 && in(prev));
-      const bool ends = me && !(next.bin == cur.bin + 1 && in(next));
-      const unsigned sm = __ballot_sync(0xffffffffu, starts), em = __ballot_sync(0xffffffffu, ends);
-      const unsigned below = (1u << lane) - 1u;
-      if (starts) {
-        const int r = count[L] + __popc(sm & below);
-        if (r < kRunCap) fr.lo[L][r] = cur.bin;
-      }
-      if (ends) {  // the run that ends here started at or before this lane: its index is (#starts up to and including me) - 1
-        const int r = count[L] + __popc(sm & (below | (1u << lane))) - 1;
-        if (r < kRunCap) fr.hi[L][r] = cur.bin;
-      }
-      count[L] += __popc(sm);
-      (void)em;
-    }
-  }
-  if (lane == 0) {
-    fr.count[0] = count[0];
-    fr.count[1] = count[1];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // k_track
 // ------------------------------------------------------------------------------------------------------------
 struct TrackShared {
   int n;                            // live signals
   int key[kMaxSignals];
   long long first[kMaxSignals], last[kMaxSignals];
-  unsigned int hit[kKeyChunk][kTrackWords];  // bit f of word w: frame (block start + 32 w + f) has a stop-level bin in the key's window
-  int event_frame;                  // first event frame found in this evaluation (or INT_MAX)
-  int error;
-  // event frame scratch
-  int n_cand;
+  unsigned int hit[kMaxSignals][kTrackWords];  // bit f of word w: frame (block start + 32 w + f) has a stop-level bin in the key's window
+  unsigned int evmask[kTrackWords];             // event frames of the block under the current key set
+  unsigned int runs[2][kRunCap][kTrackFrames];  // per frame (thread): packed runs of [0] stop-level bins, [1] start-level candidates
+  int votes[128], tied[128];                    // getBestIndex scratch (thread 0)
+  int changed, error, best_key;
+  int row_idx[128];                 // getBestIndex: first maximum of each ring row (-1 = below the start level)
+  // event-frame scratch (the output lists reuse it after the last frame)
+  int n_cand, n_open;
   int cand_bin[kMaxCand];
   float cand_val[kMaxCand];
   int cand_order[kMaxCand];
-  float tx_power[kMaxSignals];
-  int tx_order[kMaxSignals];
+  int open_rank[kMaxCand];          // ranks of the candidates no key covered when the frame began, ascending
+  unsigned char open_flag[kMaxCand];
 };
 
-// getBestIndex (transmission.cpp:132-154) for candidate bin `index` at in-push frame `frame`, by one warp
-__device__ int track_best_index(const TrackArgs& a, int index, int frame, int lane) {
+// getBestIndex (transmission.cpp:132-154) for candidate bin `index` at in-push frame `frame`, by the whole CTA: one warp per ring
+// row finds the row's first maximum around the bin, thread 0 takes the mode of the rows that reach the start level.
+__device__ void track_best_index(const TrackArgs& a, TrackShared& s, int index, int frame) {
   const TrackParams& p = a.p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = p.group_y, rows = total - total / 2;  // rows [total/2, total) of the ring = the newest `rows` frames
   const int lo = max(0, index - p.group_size / 2), hi = min(p.n - 1, index + p.group_size / 2);
-  constexpr int kMaxVotes = 128;  // rows = Y - Y/2 <= 128 (grouping_y <= 256 is validated on the host)
-  int votes[kMaxVotes];            // identical in every lane of the warp
-  int n_votes = 0;
-  for (int r = 0; r < rows; ++r) {
+  for (int r = warp; r < rows; r += kTrackThreads / 32) {
     const int f = frame - rows + 1 + r;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -198,43 +161,62 @@ __device__ int track_best_index(const TrackArgs& a, int index, int frame, int la
       argmax_combine(bv, bi, v, b);  // first maximum: ties keep the lower bin (getMaxIndex, collection_utils.h:9-14)
     }
     warp_argmax(bv, bi);
-    if (p.start_level <= bv && n_votes < kMaxVotes) votes[n_votes++] = bi;
+    if (lane == 0) s.row_idx[r] = (p.start_level <= bv) ? bi : -1;
   }
-  if (n_votes == 0) return index;  // the reference indexes an empty vector here (collection_utils.h:46-49); defined as "keep the candidate"
-  // mostFrequentValue (collection_utils.h:30-50): the mode; among equally frequent values the one at position size/2 of the
-  // ascending tied set
-  for (int i = 1; i < n_votes; ++i) {  // insertion sort, ascending
-    const int v = votes[i];
-    int j = i - 1;
-    while (j >= 0 && votes[j] > v) {
-      votes[j + 1] = votes[j];
-      --j;
+  __syncthreads();
+  if (tid == 0) {
+    // mostFrequentValue (collection_utils.h:30-50): the mode; among equally frequent values the one at position size/2 of the
+    // ascending tied set. No vote at all: the reference indexes an empty vector (collection_utils.h:46-49); defined as "keep the bin".
+    int* votes = s.votes;
+    int* tied = s.tied;
+    int n_votes = 0;
+    for (int r = 0; r < rows; ++r) {
+      if (s.row_idx[r] >= 0) votes[n_votes++] = s.row_idx[r];
     }
-    votes[j + 1] = v;
-  }
-  int best = 0, n_tied = 0;
-  int tied[kMaxVotes];
-  for (int i = 0; i < n_votes;) {
-    int j = i;
-    while (j < n_votes && votes[j] == votes[i]) ++j;
-    const int run = j - i;
-    if (run > best) {
-      best = run;
-      n_tied = 0;
+    int result = index;
+    if (n_votes > 0) {
+      for (int i = 1; i < n_votes; ++i) {  // insertion sort, ascending
+        const int v = votes[i];
+        int j = i - 1;
+        while (j >= 0 && votes[j] > v) {
+          votes[j + 1] = votes[j];
+          --j;
+        }
+        votes[j + 1] = v;
+      }
+      int best = 0, n_tied = 0;
+      for (int i = 0; i < n_votes;) {
+        int j = i;
+        while (j < n_votes && votes[j] == votes[i]) ++j;
+        if (j - i > best) {
+          best = j - i;
+          n_tied = 0;
+        }
+        if (j - i == best) tied[n_tied++] = votes[i];
+        i = j;
+      }
+      result = tied[n_tied / 2];
     }
-    if (run == best) tied[n_tied++] = votes[i];
-    i = j;
+    s.best_key = result;
   }
-  return tied[n_tied / 2];
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTrackThreads) k_track(const TrackArgs a) {
+__global__ void __launch_bounds__(kTrackThreads, 1) k_track(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char track_smem[];
   TrackShared& s = *reinterpret_cast<TrackShared*>(track_smem);
   const TrackParams& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = a.n_frames;
   const int gh = p.group_size / 2, margin = track_margin(p.group_size);
+  const long long clock_begin = clock64();
+  int n_evals = 0, n_events = 0, n_best = 0;  // (thread 0's copies are reported)
+  long long ph[4] = {0, 0, 0, 0}, ph_t = clock_begin;
+  auto lap = [&](int i) {
+    const long long c = clock64();
+    ph[i] += c - ph_t;
+    ph_t = c;
+  };
 
   // ---- load the map ----
   if (tid == 0) {
@@ -249,211 +231,286 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const TrackArgs a) {
   }
   __syncthreads();
 
-  int ts = 0;  // first frame not yet applied (uniform)
-  while (ts < T) {
-    const int bs = ts & ~(kTrackFrames - 1);              // block of frames [bs, bs + 1024) holding ts
+  for (int bs = 0; bs < T; bs += kTrackFrames) {  // blocks of 1024 frames, one thread per frame
     const int be = min(T, bs + kTrackFrames);
-    const int t = bs + tid;                               // my frame
-    const bool mine = t >= ts && t < be;
-    const int K = s.n;
-    if (tid == 0) s.event_frame = 0x7fffffff;
-    __syncthreads();
-    const FrameRuns* fr = mine ? a.runs + t : nullptr;
-    const int n_stop = mine ? fr->count[0] : 0, n_start = mine ? fr->count[1] : 0;
+    const int t = bs + tid;
+    const bool in_block = t < be;
     const long long now = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + t);
-    bool event = false;
-    if (mine) {
-      if (n_stop > kRunCap || n_start > kRunCap) event = true;  // complex frame: replayed from its raw entries
-      // addSignals can fire when a candidate bin lies outside every key's margin interval (containsWithMargin)
-      for (int r = 0; r < min(n_start, kRunCap) && !event; ++r) {
-        int pos = fr->lo[1][r];
-        const int end = fr->hi[1][r];
-        int i = track_lower_bound(s.key, K, pos - margin);
-        while (pos <= end) {
-          if (i >= K || s.key[i] - margin > pos) {
-            event = true;
-            break;
+    // My frame's detection entries (ascending bins) folded into runs of consecutive bins: those at or above the stop level, and the
+    // start-level candidates (in range, not ignored). One run per emitter and level, so the per-frame work of the evaluations
+    // below does not grow with the width of a signal. Kept in (local) registers for every evaluation of this block.
+    int n_stop = 0, n_start = 0;
+    if (in_block) {
+      const int e0 = a.offsets[t], e1 = a.offsets[t + 1];
+      int lo_s = 0, len_s = 0, lo_c = 0, len_c = 0;  // the open run of each level (len 0 = none)
+      auto close = [&](int level, int& count, int lo, int len) {
+        if (len > 0) {
+          if (count < kRunCap) s.runs[level][count][tid] = (static_cast<unsigned>(lo) << kRunLenBits) | static_cast<unsigned>(len - 1);
+          ++count;
+        }
+      };
+      for (int e = e0; e < e1; ++e) {
+        const DetectEntry d = a.entries[e];
+        if (p.stop_level <= d.value) {
+          if (len_s > 0 && d.bin == lo_s + len_s && len_s < (1 << kRunLenBits)) {
+            ++len_s;
+          } else {
+            close(0, n_stop, lo_s, len_s);
+            lo_s = d.bin;
+            len_s = 1;
           }
-          pos = s.key[i] + margin + 1;
-          ++i;
+        }
+        if (p.start_level <= d.value && track_candidate_bin(p, d.bin)) {
+          if (len_c > 0 && d.bin == lo_c + len_c && len_c < (1 << kRunLenBits)) {
+            ++len_c;
+          } else {
+            close(1, n_start, lo_c, len_c);
+            lo_c = d.bin;
+            len_c = 1;
+          }
         }
       }
+      close(0, n_stop, lo_s, len_s);
+      close(1, n_start, lo_c, len_c);
     }
-    // ---- pass 1: hit bits per key chunk, then the first time-out of every key ----
-    for (int c0 = 0; c0 < K || c0 == 0; c0 += kKeyChunk) {
-      const int kc = min(kKeyChunk, K - c0);
-      for (int q = 0; q < kc; ++q) {
-        const int key = s.key[c0 + q];
-        const int lo = max(0, key - gh), hi = min(p.n - 1, key + gh);
+    const bool complex_frame = n_stop > kRunCap || n_start > kRunCap;  // replayed from its raw entries
+    __syncthreads();
+    lap(0);
+    int ts = bs;  // first frame of the block not yet applied (uniform)
+    while (ts < be) {
+      // ================= evaluation: events of the frames [ts, be) under the current key set =================
+      ++n_evals;
+      const bool mine = in_block && t >= ts;
+      const int K = s.n;
+      bool event = mine && complex_frame;
+      if (mine && !event) {
+        // addSignals can fire when a candidate bin lies outside every key's margin interval (containsWithMargin)
+        for (int r = 0; r < n_start && !event; ++r) {
+          const unsigned run = s.runs[1][r][tid];
+          int pos = static_cast<int>(run >> kRunLenBits);
+          const int end = pos + static_cast<int>(run & ((1u << kRunLenBits) - 1u));
+          int i = track_lower_bound(s.key, K, pos - margin);
+          while (pos <= end) {
+            if (i >= K || s.key[i] - margin > pos) {
+              event = true;
+              break;
+            }
+            pos = s.key[i] + margin + 1;
+            ++i;
+          }
+        }
+      }
+      for (int q = 0; q < K; ++q) {  // hit bits of every key
+        const int lo = max(0, s.key[q] - gh), hi = min(p.n - 1, s.key[q] + gh);
         bool h = false;
-        for (int r = 0; r < min(n_stop, kRunCap); ++r) h = h || (fr->lo[0][r] <= hi && fr->hi[0][r] >= lo);
-        const unsigned m = __ballot_sync(0xffffffffu, mine && h);
+        if (mine) {
+          for (int r = 0; r < min(n_stop, kRunCap); ++r) {
+            const unsigned run = s.runs[0][r][tid];
+            const int rl = static_cast<int>(run >> kRunLenBits);
+            h = h || (rl <= hi && rl + static_cast<int>(run & ((1u << kRunLenBits) - 1u)) >= lo);
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, h);
         if (lane == 0) s.hit[q][warp] = m;
       }
       __syncthreads();
       if (mine && !event) {
-        for (int q = 0; q < kc; ++q) {
+        for (int q = 0; q < K; ++q) {
           // time of the key's latest hit at or before my frame (Signal::newData sets m_lastDataTime = now on such frames)
-          long long last = s.last[c0 + q];
+          long long last = s.last[q];
           unsigned m = s.hit[q][warp] & (0xffffffffu >> (31 - lane));
           int w = warp;
           while (m == 0u && w > 0) m = s.hit[q][--w];
           if (m != 0u) last = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + bs + 32 * w + (31 - __clz(m)));
-          if (last + p.timeout <= now || s.first[c0 + q] + p.max_time <= now) {  // isTimeout / isMaximalTime, signal.cpp:28-30
+          if (last + p.timeout <= now || s.first[q] + p.max_time <= now) {  // isTimeout / isMaximalTime, signal.cpp:28-30
             event = true;
             break;
           }
         }
       }
-      if (c0 + kKeyChunk < K) __syncthreads();  // the hit words are rewritten by the next chunk
-      if (K == 0) break;
-    }
-    if (event) atomicMin(&s.event_frame, t);
-    __syncthreads();
-    const int te = min(s.event_frame, be);  // frames [ts, te) are steady
-    // ---- pass 2: commit the steady frames: every key's m_lastDataTime ----
-    for (int c0 = 0; c0 < K; c0 += kKeyChunk) {
-      const int kc = min(kKeyChunk, K - c0);
-      if (K > kKeyChunk) {  // several chunks: the words of this chunk have to be rebuilt
-        __syncthreads();
-        for (int q = 0; q < kc; ++q) {
-          const int key = s.key[c0 + q];
-          const int lo = max(0, key - gh), hi = min(p.n - 1, key + gh);
-          bool h = false;
-          for (int r = 0; r < min(n_stop, kRunCap); ++r) h = h || (fr->lo[0][r] <= hi && fr->hi[0][r] >= lo);
-          const unsigned m = __ballot_sync(0xffffffffu, mine && h);
-          if (lane == 0) s.hit[q][warp] = m;
+      {
+        const unsigned m = __ballot_sync(0xffffffffu, event);
+        if (lane == 0) s.evmask[warp] = m;
+      }
+      if (tid == 0) s.changed = 0;
+      __syncthreads();
+      lap(1);
+      if (a.debug && tid == 0) {
+        printf("[k_track] eval ts=%d be=%d K=%d evmask %08x %08x hit0 %08x %08x", ts, be, K, s.evmask[0], s.evmask[1], K > 0 ? s.hit[0][0] : 0u, K > 0 ? s.hit[0][1] : 0u);
+        for (int q = 0; q < K; ++q) printf(" key%d last %lld", s.key[q], s.last[q]);
+        printf("\n");
+      }
+      // ================= walk the event frames in order until one of them changes the key set =================
+      int cur = ts;
+      while (true) {
+        int te = be;  // next event frame at or after cur
+        {
+          int w = (cur - bs) >> 5;
+          unsigned m = w < kTrackWords ? (s.evmask[w] & (0xffffffffu << ((cur - bs) & 31))) : 0u;
+          while (m == 0u && ++w < kTrackWords) m = s.evmask[w];
+          if (m != 0u) te = min(be, bs + 32 * w + (__ffs(m) - 1));
+        }
+        // commit the steady frames [cur, te): every key's m_lastDataTime = its newest hit among them
+        if (tid < K && te > cur) {
+          const int last_f = te - 1 - bs;
+          int w = last_f >> 5;
+          unsigned m = s.hit[tid][w] & (0xffffffffu >> (31 - (last_f & 31)));
+          const int w_min = (cur - bs) >> 5;
+          while (m == 0u && w > w_min) m = s.hit[tid][--w];
+          if (w == w_min) m &= 0xffffffffu << ((cur - bs) & 31);
+          if (m != 0u) s.last[tid] = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + bs + 32 * w + (31 - __clz(m)));
         }
         __syncthreads();
-      }
-      if (tid < kc && te > ts) {
-        const int last_f = te - 1 - bs;  // newest steady frame, relative to the block
-        int w = last_f >> 5;
-        unsigned m = s.hit[tid][w] & (0xffffffffu >> (31 - (last_f & 31)));
-        while (m == 0u && w > 0) m = s.hit[tid][--w];
-        if (m != 0u) s.last[c0 + tid] = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + bs + 32 * w + (31 - __clz(m)));
-      }
-    }
-    __syncthreads();
-    if (te >= be) {
-      ts = be;
-      continue;
-    }
-    // ---- the event frame te, exactly as Transmission::process orders it (transmission.cpp:57-68) ----
-    const long long ev_now = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + te);
-    const int e0 = a.offsets[te], e1 = a.offsets[te + 1];
-    if (tid == 0) s.n_cand = 0;
-    __syncthreads();
-    // addSignals: candidates = start-level bins in range and not ignored, strongest first (transmission.cpp:88-96)
-    for (int e = e0 + tid; e < e1; e += kTrackThreads) {
-      const DetectEntry d = a.entries[e];
-      if (p.start_level <= d.value && track_candidate_bin(p, d.bin)) {
-        const int i = atomicAdd(&s.n_cand, 1);
-        if (i < kMaxCand) {
-          s.cand_bin[i] = d.bin;
-          s.cand_val[i] = d.value;
+        if (te >= be) {
+          ts = be;
+          break;
         }
-      }
-    }
-    __syncthreads();
-    if (s.n_cand > kMaxCand && tid == 0) s.error |= 2;
-    const int nc = min(s.n_cand, kMaxCand);
-    for (int i = tid; i < nc; i += kTrackThreads) {  // rank sort: (value desc, bin asc); bins are distinct
-      const float v = s.cand_val[i];
-      const int b = s.cand_bin[i];
-      int rank = 0;
-      for (int k = 0; k < nc; ++k) rank += (s.cand_val[k] > v || (s.cand_val[k] == v && s.cand_bin[k] < b)) ? 1 : 0;
-      s.cand_order[rank] = i;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      for (int c = 0; c < nc; ++c) {
-        const int idx = s.cand_bin[s.cand_order[c]];
-        if (track_within_margin(s.key, s.n, idx, margin)) continue;  // containsWithMargin, transmission.cpp:99
-        const int key = track_best_index(a, idx, te, lane);
-        if (lane == 0) {
-          const int pos = track_lower_bound(s.key, s.n, key);
-          if (!(pos < s.n && s.key[pos] == key)) {  // std::map::insert keeps an existing element
-            if (s.n >= kMaxSignals) {
-              s.error |= 1;
-            } else {
-              for (int i = s.n; i > pos; --i) {
-                s.key[i] = s.key[i - 1];
-                s.first[i] = s.first[i - 1];
-                s.last[i] = s.last[i - 1];
-              }
-              s.key[pos] = key;
-              s.first[pos] = ev_now;  // Signal(now): m_firstDataTime = m_lastDataTime = now (signal.cpp:6-14)
-              s.last[pos] = ev_now;
-              s.n += 1;
+        // ---- the event frame te, exactly as Transmission::process orders it (transmission.cpp:57-68) ----
+        ++n_events;
+        if (a.debug && tid == 0) printf("[k_track]   event frame %d (cur %d)\n", te, cur);
+        const long long ev_now = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + te);
+        const int e0 = a.offsets[te], e1 = a.offsets[te + 1];
+        if (tid == 0) {
+          s.n_cand = 0;
+          s.n_open = 0;
+        }
+        __syncthreads();
+        // addSignals: candidates = start-level bins in range and not ignored, strongest first (transmission.cpp:88-96)
+        for (int e = e0 + tid; e < e1; e += kTrackThreads) {
+          const DetectEntry d = a.entries[e];
+          if (p.start_level <= d.value && track_candidate_bin(p, d.bin)) {
+            const int i = atomicAdd(&s.n_cand, 1);
+            if (i < kMaxCand) {
+              s.cand_bin[i] = d.bin;
+              s.cand_val[i] = d.value;
             }
           }
         }
-        __syncwarp();
+        __syncthreads();
+        if (s.n_cand > kMaxCand && tid == 0) s.error |= 2;
+        const int nc = min(s.n_cand, kMaxCand);
+        for (int i = tid; i < nc; i += kTrackThreads) {  // rank sort: (value desc, bin asc); bins are distinct
+          const float v = s.cand_val[i];
+          const int b = s.cand_bin[i];
+          int rank = 0;
+          for (int k = 0; k < nc; ++k) rank += (s.cand_val[k] > v || (s.cand_val[k] == v && s.cand_bin[k] < b)) ? 1 : 0;
+          s.cand_order[rank] = i;
+        }
+        __syncthreads();
+        // candidates that no key covers right now (containsWithMargin, transmission.cpp:99), in rank order
+        for (int r = tid; r < nc; r += kTrackThreads) s.open_flag[r] = track_within_margin(s.key, s.n, s.cand_bin[s.cand_order[r]], margin) ? 0 : 1;
+        __syncthreads();
+        if (tid == 0) {
+          int m = 0;
+          for (int r = 0; r < nc; ++r) {
+            if (s.open_flag[r]) s.open_rank[m++] = r;
+          }
+          s.n_open = m;
+        }
+        __syncthreads();
+        const int n_open = s.n_open;
+        for (int u = 0; u < n_open; ++u) {
+          const int idx = s.cand_bin[s.cand_order[s.open_rank[u]]];
+          if (track_within_margin(s.key, s.n, idx, margin)) continue;  // a key inserted for a stronger candidate covers it now (uniform)
+          ++n_best;
+          track_best_index(a, s, idx, te);
+          if (tid == 0) {
+            const int key = s.best_key;
+            const int pos = track_lower_bound(s.key, s.n, key);
+            if (!(pos < s.n && s.key[pos] == key)) {  // std::map::insert keeps an existing element
+              if (s.n >= kMaxSignals) {
+                s.error |= 1;
+              } else {
+                for (int i = s.n; i > pos; --i) {
+                  s.key[i] = s.key[i - 1];
+                  s.first[i] = s.first[i - 1];
+                  s.last[i] = s.last[i - 1];
+                }
+                s.key[pos] = key;
+                s.first[pos] = ev_now;  // Signal(now): m_firstDataTime = m_lastDataTime = now (signal.cpp:6-14)
+                s.last[pos] = ev_now;
+                s.n += 1;
+                s.changed = 1;
+              }
+            }
+          }
+          __syncthreads();
+        }
+        // updateSignals: a stop-level bin inside the key's window refreshes m_lastDataTime (transmission.cpp:113-130, signal.cpp:16-24)
+        for (int i = tid; i < s.n; i += kTrackThreads) {
+          const int lo = max(0, s.key[i] - gh), hi = min(p.n - 1, s.key[i] + gh);
+          int x = e0, y = e1;
+          while (x < y) {  // first entry of the frame with bin >= lo
+            const int m = (x + y) >> 1;
+            if (a.entries[m].bin < lo) x = m + 1; else y = m;
+          }
+          bool h = false;
+          for (int e = x; e < e1 && a.entries[e].bin <= hi; ++e) h = h || (p.stop_level <= a.entries[e].value);
+          if (h) s.last[i] = ev_now;
+        }
+        __syncthreads();
+        // clearSignals (transmission.cpp:70-86)
+        if (tid == 0) {
+          int w = 0;
+          for (int i = 0; i < s.n; ++i) {
+            if (s.last[i] + p.timeout <= ev_now || s.first[i] + p.max_time <= ev_now) {
+              s.changed = 1;
+              continue;
+            }
+            s.key[w] = s.key[i];
+            s.first[w] = s.first[i];
+            s.last[w] = s.last[i];
+            ++w;
+          }
+          s.n = w;
+        }
+        __syncthreads();
+        cur = te + 1;
+        if (s.changed) {  // the hit words and the predicted events belong to the old key set: evaluate again from here
+          ts = cur;
+          break;
+        }
+        if (cur >= be) {
+          ts = be;
+          break;
+        }
       }
+      __syncthreads();
+      lap(2);
     }
-    __syncthreads();
-    // updateSignals: a stop-level bin inside the key's window refreshes m_lastDataTime (transmission.cpp:113-130, signal.cpp:16-24)
-    for (int i = tid; i < s.n; i += kTrackThreads) {
-      const int lo = max(0, s.key[i] - gh), hi = min(p.n - 1, s.key[i] + gh);
-      int x = e0, y = e1;
-      while (x < y) {  // first entry of the frame with bin >= lo
-        const int m = (x + y) >> 1;
-        if (a.entries[m].bin < lo) x = m + 1; else y = m;
-      }
-      bool h = false;
-      for (int e = x; e < e1 && a.entries[e].bin <= hi; ++e) h = h || (p.stop_level <= a.entries[e].value);
-      if (h) s.last[i] = ev_now;
-    }
-    __syncthreads();
-    // clearSignals (transmission.cpp:70-86)
-    if (tid == 0) {
-      int w = 0;
-      for (int i = 0; i < s.n; ++i) {
-        if (s.last[i] + p.timeout <= ev_now || s.first[i] + p.max_time <= ev_now) continue;
-        s.key[w] = s.key[i];
-        s.first[w] = s.first[i];
-        s.last[w] = s.last[i];
-        ++w;
-      }
-      s.n = w;
-    }
-    __syncthreads();
-    ts = te + 1;
   }
 
   // ---- after the last frame: m_power, getSortedTransmissions, state back to global memory ----
   const int K = s.n;
-  const long long last_now = T > 0 ? track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + T - 1) : a.result->last_now;
+  float* tx_power = s.cand_val;  // (the event scratch is free now)
+  int* tx_order = s.cand_order;
+  const long long last_now = T > 0 ? track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + T - 1) : 0;
   for (int i = tid; i < K; i += kTrackThreads) {
-    float pw = a.state->power[i];  // (overwritten below when the push had frames)
-    if (T > 0) {
-      const int lo = max(0, s.key[i] - gh), hi = min(p.n - 1, s.key[i] + gh);
-      pw = a.box_last[lo];
-      for (int b = lo + 1; b <= hi; ++b) pw = fmaxf(pw, a.box_last[b]);  // getMaxIndex(avgPower, ...): the window maximum
-    }
-    s.tx_power[i] = pw;
+    const int lo = max(0, s.key[i] - gh), hi = min(p.n - 1, s.key[i] + gh);
+    float pw = a.box_last[lo];
+    for (int b = lo + 1; b <= hi; ++b) pw = fmaxf(pw, a.box_last[b]);  // getMaxIndex(avgPower, ...): the window maximum
+    tx_power[i] = pw;
   }
   __syncthreads();
   for (int i = tid; i < K; i += kTrackThreads) {  // power descending, equal powers by ascending key
-    const float v = s.tx_power[i];
+    const float v = tx_power[i];
     int rank = 0;
-    for (int k = 0; k < K; ++k) rank += (s.tx_power[k] > v || (s.tx_power[k] == v && k < i)) ? 1 : 0;
-    s.tx_order[rank] = i;
+    for (int k = 0; k < K; ++k) rank += (tx_power[k] > v || (tx_power[k] == v && k < i)) ? 1 : 0;
+    tx_order[rank] = i;
   }
   __syncthreads();
   for (int r = tid; r < K; r += kTrackThreads) {
-    const int i = s.tx_order[r];
+    const int i = tx_order[r];
     b2s_transmission tx;
     tx.shift_hz = track_tuned(track_index_to_shift(p, s.key[i]), p.tuning_step);
     tx.flush = (s.last[i] == last_now && s.first[i] + p.min_time <= last_now) ? 1 : 0;  // Signal::needFlush, signal.cpp:26,32
     tx.key = s.key[i];
-    tx.power = s.tx_power[i];
+    tx.power = tx_power[i];
     a.result->tx[r] = tx;
     a.state->key[i] = s.key[i];
     a.state->first[i] = s.first[i];
     a.state->last[i] = s.last[i];
-    a.state->power[i] = s.tx_power[i];
+    a.state->power[i] = tx_power[i];
   }
   if (tid == 0) {
     a.state->n = K;
@@ -463,6 +520,12 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const TrackArgs a) {
     a.result->max_count = a.max_count ? *a.max_count : 0;
     a.result->error = s.error;
     a.result->last_now = last_now;
+    a.result->n_evals = n_evals;
+    a.result->n_events = n_events;
+    a.result->n_best = n_best;
+    lap(3);
+    a.result->cycles = clock64() - clock_begin;
+    for (int i = 0; i < 4; ++i) a.result->phase[i] = ph[i];
   }
 }
 

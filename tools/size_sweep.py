@@ -41,7 +41,8 @@ def main():
         p = band.get_profile(reset=True)
         k1, k2 = p.spectral_ms / p.spectral_launches, p.detect_ms / p.detect_launches
         row = {"n": n, "frames": T, "k1_ms": round(k1, 4), "k2_ms": round(k2, 4), "k1_gbs": round(6 * T * n / k1 / 1e6, 1), "k2_gbs": round(4 * T * n / k2 / 1e6, 1),
-               "tracker_ms": round(p.tracker_host_ms / reps, 4)}
+               "host_ms": round(p.tracker_host_ms / reps, 4), "k4_ms": round(p.track_ms / max(p.track_launches, 1), 4),
+               "k4_evals": p.track_evals / max(p.track_launches, 1), "k4_events": p.track_events / max(p.track_launches, 1)}
         print(json.dumps(row), flush=True)
         out.append(row)
         band.close()
