@@ -46,6 +46,7 @@ struct PushSlot {
   DevBuf<int> cand_flag;
   // device tracker (K4): runs of the frames' entries, the last frame's boxcar row, the push's result
   DevBuf<float> box_last;
+  DevBuf<int> run_lo, run_hi, run_count;  // RunFold arrays of the chunk
   DevBuf<TrackResult> d_result;
   PinBuf<TrackResult> h_result;
   cudaEvent_t sorted_done = nullptr, tev[2] = {nullptr, nullptr};
@@ -74,7 +75,7 @@ struct PushSlot {
   void release() {
     psd.release(); ckpt.release(); dense_q.release(); dense_avg.release(); dense_box.release(); peak_val.release();
     peak_idx.release(); offsets.release(); max_count.release(); sorted.release(); spec_rows.release();
-    box_last.release(); d_result.release(); h_result.release();
+    box_last.release(); run_lo.release(); run_hi.release(); run_count.release(); d_result.release(); h_result.release();
     if (sorted_done) cudaEventDestroy(sorted_done);
     for (auto& e : tev) {
       if (e) cudaEventDestroy(e);
@@ -358,6 +359,9 @@ struct b2s_band : public DeviceQueries {
       CU(cudaEventCreateWithFlags(&s.gpu_done, cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&s.sorted_done, cudaEventDisableTiming));
       if ((rc = s.box_last.alloc(n))) return rc;
+      if ((rc = s.run_lo.alloc(static_cast<size_t>(2 * kRunCap) * max_frames))) return rc;
+      if ((rc = s.run_hi.alloc(static_cast<size_t>(2 * kRunCap) * max_frames))) return rc;
+      if ((rc = s.run_count.alloc(static_cast<size_t>(2) * max_frames))) return rc;
       if ((rc = s.d_result.alloc(1))) return rc;
       if ((rc = s.h_result.alloc(1))) return rc;
     }
@@ -753,7 +757,24 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     // order the per-frame slot lists by bin into one dense array
     k_entries_prefix<<<1, 1024, 0, stream>>>(d_slot_count.p, slot_capacity, T, s.offsets.p, s.max_count.p);
     CU(cudaGetLastError());
-    k_entries_sort<<<(T * 32 + 255) / 256, 256, 0, stream>>>(d_slots.p, d_slot_count.p, slot_capacity, T, s.offsets.p, s.sorted.p);
+    RunFold fold{};
+    TrackParams tp{};
+    if (!s.host_track) {  // K4 works on runs of the ordered entries
+      tp = track_params();
+      fold.stop_level = tp.stop_level;
+      fold.start_level = tp.start_level;
+      fold.bin_lo = tp.bin_lo;
+      fold.bin_hi = tp.bin_hi;
+      fold.n_ignored = tp.n_ignored;
+      for (int i = 0; i < tp.n_ignored; ++i) {
+        fold.ignored_lo[i] = tp.ignored_lo[i];
+        fold.ignored_hi[i] = tp.ignored_hi[i];
+      }
+      fold.lo = s.run_lo.p;
+      fold.hi = s.run_hi.p;
+      fold.count = s.run_count.p;
+    }
+    k_entries_sort<<<(T * 32 + 255) / 256, 256, 0, stream>>>(d_slots.p, d_slot_count.p, slot_capacity, T, s.offsets.p, s.sorted.p, fold);
     CU(cudaGetLastError());
     if (profiling) CU(cudaEventRecord(s.ev[3], stream));
   }
@@ -763,6 +784,9 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     CU(cudaStreamWaitEvent(track_stream, s.sorted_done, 0));
     TrackArgs ta{};
     ta.p = track_params();
+    ta.run_lo = s.run_lo.p;
+    ta.run_hi = s.run_hi.p;
+    ta.run_count = s.run_count.p;
     ta.n_frames = T;
     ta.t0_ms = t0_ms;
     ta.period_ms = period_ms;

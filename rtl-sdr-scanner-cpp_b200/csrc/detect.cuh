@@ -697,7 +697,30 @@ __global__ void __launch_bounds__(1024) k_entries_prefix(const int* slot_count, 
   atomicMax(max_count, biggest);
 }
 
-__global__ void __launch_bounds__(256) k_entries_sort(const DetectEntry* slots, const int* slot_count, int capacity, int n_frames, const int* offsets, DetectEntry* out) {
+// Runs of consecutive bins of a frame's ordered entries, per level: [0] bins at or above the stop level, [1] start-level candidates
+// (in range, not ignored: isIndexInRange / isIndexIgnored as bin intervals). K4 works on these instead of the raw entries, so
+// its per-frame work does not grow with the width of a signal. Folded here because this kernel has a warp per frame and the whole
+// GPU; K4 is a single CTA.
+constexpr int kRunCap = 8;  // runs kept per frame and level; K4 replays a frame with more from its raw entries
+struct RunFold {
+  float stop_level, start_level;
+  int bin_lo, bin_hi;                                                       // candidate bins: inside the scanned range ...
+  int n_ignored, ignored_lo[16], ignored_hi[16];                            // ... and outside every ignored interval (bins, inclusive)
+  int* lo;     // [2][kRunCap][n_frames] first bin of run r of level L of frame t at ((L * kRunCap + r) * n_frames + t)
+  int* hi;     // same layout: last bin
+  int* count;  // [2][n_frames]; may exceed kRunCap
+};
+__device__ __forceinline__ bool run_member(const RunFold& f, int level, const DetectEntry& d) {
+  if (d.bin < 0) return false;
+  if (level == 0) return f.stop_level <= d.value;
+  if (!(f.start_level <= d.value) || d.bin < f.bin_lo || d.bin > f.bin_hi) return false;
+  for (int r = 0; r < f.n_ignored; ++r) {
+    if (f.ignored_lo[r] <= d.bin && d.bin <= f.ignored_hi[r]) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_entries_sort(const DetectEntry* slots, const int* slot_count, int capacity, int n_frames, const int* offsets, DetectEntry* out, const RunFold fold) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_frames) return;
   const int count = min(slot_count[warp], capacity);
@@ -708,6 +731,38 @@ __global__ void __launch_bounds__(256) k_entries_sort(const DetectEntry* slots, 
     int rank = 0;
     for (int k = 0; k < count; ++k) rank += (src[k].bin < e.bin) ? 1 : 0;
     dst[rank] = e;
+  }
+  if (!fold.count) return;
+  __syncwarp();  // the ordered list is visible to the whole warp
+  int n_runs[2] = {0, 0};
+  for (int base = 0; base < count; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < count;
+    const DetectEntry none{-10, 0.0f};
+    const DetectEntry cur = valid ? dst[e] : none;
+    const DetectEntry prev = (valid && e > 0) ? dst[e - 1] : none;
+    const DetectEntry next = (valid && e + 1 < count) ? dst[e + 1] : none;
+#pragma unroll
+    for (int L = 0; L < 2; ++L) {
+      const bool me = valid && run_member(fold, L, cur);
+      const bool starts = me && !(prev.bin == cur.bin - 1 && run_member(fold, L, prev));
+      const bool ends = me && !(next.bin == cur.bin + 1 && run_member(fold, L, next));
+      const unsigned sm = __ballot_sync(0xffffffffu, starts);
+      const unsigned below = (1u << lane) - 1u;
+      if (starts) {
+        const int r = n_runs[L] + __popc(sm & below);
+        if (r < kRunCap) fold.lo[static_cast<size_t>(L * kRunCap + r) * n_frames + warp] = cur.bin;
+      }
+      if (ends) {  // the run that ends here started at or before this lane: (#starts up to and including me) - 1
+        const int r = n_runs[L] + __popc(sm & (below | (1u << lane))) - 1;
+        if (r < kRunCap) fold.hi[static_cast<size_t>(L * kRunCap + r) * n_frames + warp] = cur.bin;
+      }
+      n_runs[L] += __popc(sm);
+    }
+  }
+  if (lane == 0) {
+    fold.count[warp] = n_runs[0];
+    fold.count[n_frames + warp] = n_runs[1];
   }
 }
 

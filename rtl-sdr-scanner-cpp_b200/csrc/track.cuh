@@ -26,7 +26,6 @@
 namespace b2s {
 
 constexpr int kMaxSignals = 256;   // live signals per band held by K4; beyond it the push fails loudly (B2S_E_OVERFLOW)
-constexpr int kRunCap = 8;         // runs kept per frame and level; a frame with more is replayed from its raw entries
 constexpr int kRunLenBits = 14;    // a run is packed as (first bin << 14) | (length - 1); longer stretches are cut into several runs
 constexpr int kTrackThreads = 1024, kTrackFrames = 1024, kTrackWords = kTrackFrames / 32;
 constexpr int kMaxCand = 2048;     // start-level candidates replayed in one event frame
@@ -69,6 +68,9 @@ struct TrackArgs {
   const DetectEntry* entries;  // ordered by (frame, bin)
   const int* offsets;          // [T + 1]
   const int* max_count;        // largest per-frame entry count (overflow report)
+  const int* run_lo;           // runs of the frames' entries, folded by k_entries_sort (RunFold layout)
+  const int* run_hi;
+  const int* run_count;
   const float* box_last;       // [N] boxcar row of the last frame
   // getBestIndex inputs: noise-subtracted rows = the Averager ring
   const float* psd;            // [T][N]
@@ -126,6 +128,7 @@ struct TrackShared {
   unsigned int hit[kMaxSignals][kTrackWords];  // bit f of word w: frame (block start + 32 w + f) has a stop-level bin in the key's window
   unsigned int evmask[kTrackWords];             // event frames of the block under the current key set
   unsigned int runs[2][kRunCap][kTrackFrames];  // per frame (thread): packed runs of [0] stop-level bins, [1] start-level candidates
+  long long time[kTrackFrames];                 // frame clock of the block's frames
   int votes[128], tied[128];                    // getBestIndex scratch (thread 0)
   int changed, error, best_key;
   int row_idx[128];                 // getBestIndex: first maximum of each ring row (-1 = below the start level)
@@ -235,44 +238,29 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track(const TrackArgs a) {
     const int be = min(T, bs + kTrackFrames);
     const int t = bs + tid;
     const bool in_block = t < be;
-    const long long now = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + t);
-    // My frame's detection entries (ascending bins) folded into runs of consecutive bins: those at or above the stop level, and the
-    // start-level candidates (in range, not ignored). One run per emitter and level, so the per-frame work of the evaluations
-    // below does not grow with the width of a signal. Kept in (local) registers for every evaluation of this block.
+    // My frame's runs (consecutive bins at or above the stop level / start-level candidates, folded by k_entries_sort), packed
+    // into shared memory for every evaluation of this block; s.time holds the frames' clock (FP64 is slow here: once per frame)
     int n_stop = 0, n_start = 0;
+    s.time[tid] = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + t);
+    bool long_run = false;
     if (in_block) {
-      const int e0 = a.offsets[t], e1 = a.offsets[t + 1];
-      int lo_s = 0, len_s = 0, lo_c = 0, len_c = 0;  // the open run of each level (len 0 = none)
-      auto close = [&](int level, int& count, int lo, int len) {
-        if (len > 0) {
-          if (count < kRunCap) s.runs[level][count][tid] = (static_cast<unsigned>(lo) << kRunLenBits) | static_cast<unsigned>(len - 1);
-          ++count;
-        }
-      };
-      for (int e = e0; e < e1; ++e) {
-        const DetectEntry d = a.entries[e];
-        if (p.stop_level <= d.value) {
-          if (len_s > 0 && d.bin == lo_s + len_s && len_s < (1 << kRunLenBits)) {
-            ++len_s;
-          } else {
-            close(0, n_stop, lo_s, len_s);
-            lo_s = d.bin;
-            len_s = 1;
-          }
-        }
-        if (p.start_level <= d.value && track_candidate_bin(p, d.bin)) {
-          if (len_c > 0 && d.bin == lo_c + len_c && len_c < (1 << kRunLenBits)) {
-            ++len_c;
-          } else {
-            close(1, n_start, lo_c, len_c);
-            lo_c = d.bin;
-            len_c = 1;
+      n_stop = a.run_count[t];
+      n_start = a.run_count[T + t];
+#pragma unroll
+      for (int L = 0; L < 2; ++L) {
+        const int cnt = min(L == 0 ? n_stop : n_start, kRunCap);
+#pragma unroll
+        for (int r = 0; r < kRunCap; ++r) {
+          if (r < cnt) {
+            const int lo = a.run_lo[static_cast<size_t>(L * kRunCap + r) * T + t], hi = a.run_hi[static_cast<size_t>(L * kRunCap + r) * T + t];
+            long_run = long_run || hi - lo >= (1 << kRunLenBits);
+            s.runs[L][r][tid] = (static_cast<unsigned>(lo) << kRunLenBits) | static_cast<unsigned>(min(hi - lo, (1 << kRunLenBits) - 1));
           }
         }
       }
-      close(0, n_stop, lo_s, len_s);
-      close(1, n_start, lo_c, len_c);
     }
+    if (long_run) n_stop = kRunCap + 1;  // a stretch too long to pack: replay the frame from its raw entries
+    const long long now = s.time[tid];
     const bool complex_frame = n_stop > kRunCap || n_start > kRunCap;  // replayed from its raw entries
     __syncthreads();
     lap(0);
@@ -321,7 +309,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track(const TrackArgs a) {
           unsigned m = s.hit[q][warp] & (0xffffffffu >> (31 - lane));
           int w = warp;
           while (m == 0u && w > 0) m = s.hit[q][--w];
-          if (m != 0u) last = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + bs + 32 * w + (31 - __clz(m)));
+          if (m != 0u) last = s.time[32 * w + (31 - __clz(m))];
           if (last + p.timeout <= now || s.first[q] + p.max_time <= now) {  // isTimeout / isMaximalTime, signal.cpp:28-30
             event = true;
             break;
@@ -358,7 +346,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track(const TrackArgs a) {
           const int w_min = (cur - bs) >> 5;
           while (m == 0u && w > w_min) m = s.hit[tid][--w];
           if (w == w_min) m &= 0xffffffffu << ((cur - bs) & 31);
-          if (m != 0u) s.last[tid] = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + bs + 32 * w + (31 - __clz(m)));
+          if (m != 0u) s.last[tid] = s.time[32 * w + (31 - __clz(m))];
         }
         __syncthreads();
         if (te >= be) {
@@ -368,7 +356,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) k_track(const TrackArgs a) {
         // ---- the event frame te, exactly as Transmission::process orders it (transmission.cpp:57-68) ----
         ++n_events;
         if (a.debug && tid == 0) printf("[k_track]   event frame %d (cur %d)\n", te, cur);
-        const long long ev_now = track_frame_time(a.t0_ms, a.period_ms, a.frame_offset + te);
+        const long long ev_now = s.time[te - bs];
         const int e0 = a.offsets[te], e1 = a.offsets[te + 1];
         if (tid == 0) {
           s.n_cand = 0;
