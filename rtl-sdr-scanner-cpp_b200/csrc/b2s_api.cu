@@ -355,8 +355,13 @@ static int make_tile_map(CUtensorMap* out, const float* base, size_t cols, size_
   const cuuint64_t strides[1] = {cols * sizeof(float)};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t elem[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (const char* e = getenv("B2S_K2_L2PROMO")) {  // A/B measurements
+    const int v = atoi(e);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo;
+  }
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2S_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", static_cast<int>(r), box_cols, box_rows);
   return 0;
 }
@@ -670,7 +675,7 @@ int b2s_band_get_averager(b2s_band* b, float* sum, float* avg, float* ring, int3
   if (rc) return rc;
   CU(cudaStreamSynchronize(b->stream));
   const size_t n = b->cfg.fft_size, Y = b->cfg.grouping_y;
-  if (sum) CU(cudaMemcpy(sum, b->d_sum.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  if (sum) CU(cudaMemcpy(sum, b->d_sum[b->sum_cur].p, sizeof(float) * n, cudaMemcpyDeviceToHost));
   if (avg) CU(cudaMemcpy(avg, b->d_avg_last.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
   if (ring) CU(cudaMemcpy(ring, b->d_ring[b->ring_cur].p, sizeof(float) * n * Y, cudaMemcpyDeviceToHost));
   if (frames) *frames = b->avg_frames;
@@ -693,7 +698,7 @@ int b2s_band_get_noise(b2s_band* b, float* threshold, int32_t* samples, int32_t*
     }
     return 0;
   }
-  if (threshold) CU(cudaMemcpy(threshold, it->second.threshold.p, sizeof(float) * b->cfg.fft_size, cudaMemcpyDeviceToHost));
+  if (threshold) CU(cudaMemcpy(threshold, it->second.now(), sizeof(float) * b->cfg.fft_size, cudaMemcpyDeviceToHost));
   if (samples) *samples = it->second.samples;
   if (ready) *ready = it->second.ready ? 1 : 0;
   return 0;

@@ -65,6 +65,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_m
                : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared through the LSU (SASS LDGSTS); src_bytes < 16 zero-fills the rest (0: no global read)
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+// the executing thread's arrival on `bar` is triggered when all its prior cp.async operations have completed (the barrier's
+// expected count includes it: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------------------------------------

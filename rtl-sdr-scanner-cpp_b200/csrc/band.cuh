@@ -16,7 +16,9 @@
 #include <thread>
 
 struct NoiseSlot {
-  DevBuf<float> threshold;
+  DevBuf<float> threshold[2];  // [cur]: the thresholds after the last enqueued push; K2 reads [cur] and writes [cur ^ 1]
+  int cur = 0;
+  float* now() { return threshold[cur].p; }
   int samples = 0;
   bool ready = false;
 };
@@ -105,7 +107,8 @@ struct b2s_band : public DeviceQueries {
 
   SpectralTables tables;
   DevBuf<unsigned char> d_iq[2];
-  DevBuf<float> d_sum, d_ring[kRings], d_avg_last;
+  DevBuf<float> d_sum[2], d_ring[kRings], d_avg_last;  // m_sum: [sum_cur] after the last enqueued push (K2 reads it, writes the other)
+  int sum_cur = 0;
   int ring_cur = 0;  // d_ring[ring_cur] = ring after the last enqueued push
   int avg_frames = 0;
   DevBuf<DetectEntry> d_slots;
@@ -146,11 +149,14 @@ struct b2s_band : public DeviceQueries {
   ~b2s_band() {
     shutdown_worker();
     tables.release();
-    d_iq[0].release(); d_iq[1].release(); d_sum.release(); d_avg_last.release();
+    d_iq[0].release(); d_iq[1].release(); d_sum[0].release(); d_sum[1].release(); d_avg_last.release();
     for (auto& r : d_ring) r.release();
     d_slots.release(); d_slot_count.release(); d_wq_val.release(); d_wq_idx.release(); h_work.release();
     for (auto& s : slots) s.release();
-    for (auto& kv : noise) kv.second.threshold.release();
+    for (auto& kv : noise) {
+      kv.second.threshold[0].release();
+      kv.second.threshold[1].release();
+    }
     for (auto& kv : spectro) kv.second.sum.release();
     for (auto& e : copy_done) {
       if (e) cudaEventDestroy(e);
@@ -170,10 +176,11 @@ struct b2s_band : public DeviceQueries {
     auto it = noise.find(center);
     if (it == noise.end()) {
       it = noise.emplace(center, NoiseSlot{}).first;
-      int rc = it->second.threshold.alloc(cfg.fft_size);
+      int rc = it->second.threshold[0].alloc(cfg.fft_size);
+      if (!rc) rc = it->second.threshold[1].alloc(cfg.fft_size);
       if (rc) return rc;
       std::vector<float> init(cfg.fft_size, -std::numeric_limits<float>::max());  // noise_learner.cpp:16
-      CU(cudaMemcpyAsync(it->second.threshold.p, init.data(), sizeof(float) * cfg.fft_size, cudaMemcpyHostToDevice, stream));
+      CU(cudaMemcpyAsync(it->second.threshold[0].p, init.data(), sizeof(float) * cfg.fft_size, cudaMemcpyHostToDevice, stream));
       CU(cudaStreamSynchronize(stream));
     }
     *out = &it->second;
@@ -367,7 +374,8 @@ struct b2s_band : public DeviceQueries {
     }
     if ((rc = d_state.alloc(1))) return rc;
     CU(cudaMemset(d_state.p, 0, sizeof(TrackState)));
-    if ((rc = d_sum.alloc(n))) return rc;
+    if ((rc = d_sum[0].alloc(n))) return rc;
+    if ((rc = d_sum[1].alloc(n))) return rc;
     for (auto& r : d_ring) {
       if ((rc = r.alloc(Y * n))) return rc;
     }
@@ -475,7 +483,8 @@ struct b2s_band : public DeviceQueries {
   // Averager::reset (averager.cpp:27-34) / constructor state (averager.cpp:7-12)
   int reset_averager() {
     const size_t n = cfg.fft_size, Y = cfg.grouping_y;
-    CU(cudaMemsetAsync(d_sum.p, 0, sizeof(float) * n, stream));
+    CU(cudaMemsetAsync(d_sum[0].p, 0, sizeof(float) * n, stream));
+    sum_cur = 0;
     for (auto& r : d_ring) CU(cudaMemsetAsync(r.p, 0, sizeof(float) * Y * n, stream));
     std::vector<float> nd(n, kNoData);
     CU(cudaMemcpyAsync(d_avg_last.p, nd.data(), sizeof(float) * n, cudaMemcpyHostToDevice, stream));
@@ -695,10 +704,12 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.group_y = Y;
   da.group_x = cfg.grouping_x;
   da.psd = s.psd.p;
-  da.threshold = ns->threshold.p;
+  da.threshold = ns->threshold[ns->cur].p;
+  da.threshold_out = ns->threshold[ns->cur ^ 1].p;
   da.noise_samples = ns->ready ? cfg.learn_frames : ns->samples;
   da.learn_frames = cfg.learn_frames;
-  da.avg_sum = d_sum.p;
+  da.avg_sum = d_sum[sum_cur].p;
+  da.avg_sum_out = d_sum[sum_cur ^ 1].p;
   da.ring_in = d_ring[ring_in].p;
   da.ring_out = d_ring[ring_out].p;
   da.avg_frames = avg_frames;
@@ -796,7 +807,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     ta.max_count = s.max_count.p;
     ta.box_last = s.box_last.p;
     ta.psd = s.psd.p;
-    ta.threshold = ns->threshold.p;
+    ta.threshold = da.threshold_out;
     ta.noise_samples = da.noise_samples;
     ta.learn_frames = cfg.learn_frames;
     ta.ring_before = d_ring[ring_in].p;
@@ -829,7 +840,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   s.noise_samples = da.noise_samples;
   s.avg_frames_before = avg_frames;
   s.ring_before = ring_in;
-  s.threshold = ns->threshold.p;
+  s.threshold = da.threshold_out;  // the thresholds as of the end of this push
   s.center = center;
   s.n_emit = n_emit;
   s.out = out;
@@ -839,6 +850,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     ns->samples = std::min(ns->samples + T, cfg.learn_frames);
     ns->ready = ns->samples >= cfg.learn_frames;
   }
+  ns->cur ^= 1;
+  sum_cur ^= 1;
   avg_frames = std::min(avg_frames + T, Y);
   ring_cur = ring_out;
   prof.frames += T;

@@ -45,11 +45,15 @@ struct DetectArgs {
   // inputs
   const float* psd;  // [T][N] raw PSD rows from K1
   // noise state (per centre frequency)
-  float* threshold;   // [N], updated in place while learning
+  // State that a CTA's HALO columns read while the owning CTA updates it is double-buffered (in: before the push, out: after): a
+  // CTA of a later wave (N >= 32768 has more CTAs than SMs; other bands' kernels delay CTAs) must not see its neighbour's results.
+  const float* threshold;  // [N] before the push
+  float* threshold_out;    // [N] after the push (differs only while learning)
   int noise_samples;  // samples learned before this push
   int learn_frames;   // frames 0.. with noise_samples + t < learn_frames are learning frames
   // averager state
-  float* avg_sum;         // [N] m_sum, updated in place
+  const float* avg_sum;   // [N] m_sum before the push
+  float* avg_sum_out;     // [N] m_sum after the push
   const float* ring_in;   // [Y][N] ring before the push, oldest -> newest
   float* ring_out;        // [Y][N] ring after the push (a different buffer)
   int avg_frames;         // m_frames before the push
@@ -222,6 +226,12 @@ constexpr int kDetectRegs = 80;
 // the register file is split over the 4 SM sub-partitions (16384 registers each) and a CTA's warps are dealt round robin
 static_assert(((kDetectThreads / 32 + 3) / 4) * ((kDetectRegs * 32 + 511) / 512 * 512) <= 16384, "k_detect must fit the register file");
 static_assert(kDetectBinsPerCta / 2 <= kSpecThreads, "one SPEC thread per spectrogram column of a CTA");
+#ifndef B2S_K2_CPASYNC
+#define B2S_K2_CPASYNC 0  // PSD tiles through one 2-D TMA load per tile (0) or 16-byte cp.async chunks (1: measured slower, 0.265 vs 0.135 ms per CTA)
+#endif
+#ifndef B2S_K2_EARLY_EMPTY
+#define B2S_K2_EARLY_EMPTY 1
+#endif
 #ifndef B2S_K2_AVG_BUFFERS
 #define B2S_K2_AVG_BUFFERS 2
 #endif
@@ -295,8 +305,8 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     }
     rel_n = cnt;
     for (int i = 0; i < a.n_buffers; ++i) {
-      mbar_init(&p_full[i], 1);
-      mbar_init(&p_empty[i], kSumWarps + kSpecWarps);
+      mbar_init(&p_full[i], B2S_K2_CPASYNC ? 32 : 1);  // cp.async: one arrival per producer lane when its copies have landed; TMA: one + the bytes
+      mbar_init(&p_empty[i], kSumWarps + ((a.spec_out > 0 && n / a.spec_out > 1) ? kSpecWarps : 0));  // the SPEC warps only run for decimating spectrograms
     }
     fence_barrier_init();
   }
@@ -450,8 +460,8 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     }
     if (spec_owner) a.spec_sum[j] = spec;
     if (owner) {
-      a.threshold[j] = thr;
-      a.avg_sum[j] = sum;
+      a.threshold_out[j] = thr;
+      a.avg_sum_out[j] = sum;
       a.avg_last[j] = (T > 0 && a.avg_frames + T >= Y) ? __fdiv_rn(sum, static_cast<float>(Y)) : kNoData;
       // ring after the push, oldest -> newest: row i is in-push frame T - Y + i, or a surviving row of ring_in
       for (int i0 = 0; i0 < Y; i0 += 8) {
@@ -471,16 +481,36 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     }
   } else if (tid >= kProducerBase && tid < kProducerBase + 32) {
     // ============================================ PRODUCER warp ============================================
-    // one TMA tile load per tile: box = [32 frames][width columns] of the PSD tensor [max_frames][N] at (col0, t0); columns
-    // left of bin 0 / right of bin N-1 and rows past the allocation arrive as zeros (nobody reads them)
+    // Streams the tile [32 frames][width columns] of the PSD rows at (col0, t0) into the ring. Columns left of bin 0 / right of bin
+    // N-1 and rows past the push arrive as zeros (nobody reads them).
+    // Measured: one 2-D TMA load per tile (box 32 x 136 floats: 32 row pieces of 544 bytes) and 32 separate 1-D bulk copies both
+    // deliver a tile in ~1.1 us whatever the ring depth (2..6 buffers: no change) — ~65 cycles per row piece, 16 GB/s per SM, and
+    // that alone is the kernel's floor (0.135 ms). The rows are only 544 bytes long in a row-major [T][N] matrix, so the copy
+    // engine's per-request cost dominates. 16-byte cp.async chunks through the LSU (B2S_K2_CPASYNC=1) are slower still: 0.265 ms.
     int ps = 0;
     uint32_t ps_phase = 1;  // waiting for the "previous" phase passes at once during the first round
+#if B2S_K2_CPASYNC
+    const int chunks_per_row = width / 4, chunks = TF * chunks_per_row;
+#endif
     for (int tile = 0; tile < n_tiles; ++tile) {
-      mbar_wait_sleepy(&p_empty[ps], ps_phase);  // the SUM warps released the slot
+      mbar_wait_sleepy(&p_empty[ps], ps_phase);  // the SUM (and SPEC) warps released the slot
+#if B2S_K2_CPASYNC
+      float* dst = psd_tiles + ps * tile_elems;
+      const int t0 = tile * TF;
+      for (int i = lane; i < chunks; i += 32) {
+        const int row = i / chunks_per_row, c4 = (i - row * chunks_per_row) * 4;
+        const int col = col0 + c4;
+        const bool inside = t0 + row < T && col >= 0 && col < n;  // hp and N are multiples of 4: a chunk is inside or outside as a whole
+        const float* src = psd + (inside ? static_cast<size_t>(t0 + row) * n + col : 0);
+        cp_async_16(dst + row * width + c4, src, inside ? 16 : 0);  // src-size 0: the 16 bytes are zero-filled
+      }
+      cp_async_mbar_arrive(&p_full[ps]);  // this lane's arrival fires when all its copies above have landed
+#else
       if (lane == 0) {
         mbar_arrive_expect_tx(&p_full[ps], static_cast<uint32_t>(tile_elems * sizeof(float)));
         tma_load_2d(psd_tiles + ps * tile_elems, &psd_map, col0, tile * TF, &p_full[ps]);
       }
+#endif
       if (++ps == a.n_buffers) {
         ps = 0;
         ps_phase ^= 1;
@@ -491,6 +521,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     // Spectrogram::process with decimation (spectrogram.cpp:45-58): out[i] += mean(p[i d .. i d + d - 1]) per frame, and
     // Spectrogram::send (spectrogram.cpp:62-72) on the frames the host planned. d is a power of two, so the mean's division is exact.
     const int d = a.spec_out > 0 ? n / a.spec_out : 0;
+    if (d <= 1) return;                                   // nothing to do (and p_empty does not count these warps)
     const int sc = tid - kSpecBase;                       // my spectrogram column inside the CTA
     const bool on = d > 1 && sc * d < bins && j0 + sc * d < n;
     const int col = on ? (j0 + sc * d) / d : 0;           // global spectrogram column
@@ -559,6 +590,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       const int f = lane, t = t0 + f;
       float box[SEG];
       bool have = false;
+      bool released = false;  // this lane has already handed the average buffer back
       // `scaled`: box[] holds the UNDIVIDED boxcar sums of an interior segment and is compared with the sum thresholds; the
       // quotient is only formed for values that leave the kernel (entries, watch maxima, box_last, dense rows)
       bool scaled = false;
@@ -573,6 +605,12 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           if (raw) {
 #pragma unroll
             for (int i = 0; i < SEG + 2 * H; ++i) w[i] = div_const_fast<YD>(w[i]);  // averager.cpp:52-60 (0 / Y = 0 for the zero extension)
+#if B2S_K2_EARLY_EMPTY
+            // every value of the tile this lane needs has been read AND used: hand the buffer back before the serial boxcar chain, so
+            // the SUM warps are not held up by it (with two average buffers they would otherwise wait for this warp's whole tile)
+            if (tile + kAvgBuffers < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);
+            released = true;
+#endif
           }
           boxcar_segment<H>(w, box);
           if (segment_interior(bin0, n, half)) {
@@ -594,7 +632,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           }
         }
       }
-      if (tile + kAvgBuffers < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten
+      if (!released && tile + kAvgBuffers < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten
       constexpr int XD = HALF_T > 0 ? 2 * HALF_T + 1 : 1;
       auto value_of = [&](float b) { return scaled ? div_const_fast<XD>(b) : b; };  // average(avg, X)[bin], utils.cpp:49
       const float lvl_detect = scaled ? a.detect_sum : a.detect_level, lvl_start = scaled ? a.start_sum : a.start_level;
