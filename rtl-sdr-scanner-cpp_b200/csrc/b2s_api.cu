@@ -645,14 +645,7 @@ int b2s_band_reset(b2s_band* b) {
   if (!b) return fail(B2S_E_INVALID, "NULL band");
   std::lock_guard<std::mutex> lock(b->mutex);
   CU(cudaSetDevice(b->engine->device));
-  int rc = b->drain();
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(b->stream));
-  b->tracker.reset();
-  CU(cudaStreamSynchronize(b->track_stream));
-  CU(cudaMemset(b->d_state.p, 0, sizeof(TrackState)));  // signals.clear(), transmission.cpp:53
-  b->mailbox.clear();
-  return b->reset_averager();
+  return b->reset_buffers();
 }
 
 int b2s_band_set_center(b2s_band* b, int32_t center_hz, int32_t lo, int32_t hi) {

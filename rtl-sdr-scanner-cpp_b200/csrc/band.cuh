@@ -53,6 +53,7 @@ struct PushSlot {
   PinBuf<TrackResult> h_result;
   cudaEvent_t sorted_done = nullptr, tev[2] = {nullptr, nullptr};
   bool host_track = false;  // this chunk's bookkeeping runs on the host (the caller asked for every frame's list)
+  int epoch = 0;            // reset_epoch when the chunk was enqueued
   PinBuf<int> h_offsets, h_cand_flag;
   PinBuf<unsigned int> h_watch_max;
   PinBuf<DetectEntry> h_entries;
@@ -126,7 +127,8 @@ struct b2s_band : public DeviceQueries {
   Tracker tracker;
 
   // result of the most recently finished chunk (the mailbox) + statistics since the last sync
-  std::vector<b2s_transmission> mailbox;  // the complete list, strongest first
+  std::vector<b2s_transmission> mailbox;  // the complete list, strongest first (guarded by qmutex against reset_buffers)
+  int reset_epoch = 0;                    // bumped by reset_buffers
   int stat_entries = 0, stat_rows = 0;
 
   // profiling
@@ -330,11 +332,22 @@ struct b2s_band : public DeviceQueries {
       const int d = c.spectrogram_out_size > 0 ? c.fft_size / c.spectrogram_out_size : 1;
       const int hp = (c.grouping_x / 2 + 3) & ~3;
       detect_bins = 0;
-      for (int bins : {112, 128, 96, 64}) {
-        if (bins % d == 0 && bins + 2 * hp <= kSumThreads) {
-          detect_bins = bins;
-          break;
+      if (c.fft_size >= 8192) {
+        for (int bins : {112, 128, 96, 64}) {
+          if (bins % d == 0 && bins + 2 * hp <= kSumThreads) {
+            detect_bins = bins;
+            break;
+          }
         }
+      } else {
+        // a small FFT has few columns: narrower CTAs (more halo per bin, but up to one CTA per SM) instead of 37 CTAs at N = 4096
+        for (int bins = kBoxSegment; bins <= kDetectBinsPerCta; bins += kBoxSegment) {
+          if (bins % d == 0 && bins + 2 * hp <= kSumThreads && (c.fft_size + bins - 1) / bins <= e->sm_count) {
+            detect_bins = bins;
+            break;
+          }
+        }
+        if (!detect_bins && 112 % d == 0 && 112 + 2 * hp <= kSumThreads) detect_bins = 112;
       }
       if (const char* e = getenv("B2S_K2_BINS")) {  // A/B measurements
         const int bins = atoi(e);
@@ -483,15 +496,26 @@ struct b2s_band : public DeviceQueries {
   // Averager::reset (averager.cpp:27-34) / constructor state (averager.cpp:7-12)
   int reset_averager() {
     const size_t n = cfg.fft_size, Y = cfg.grouping_y;
-    CU(cudaMemsetAsync(d_sum[0].p, 0, sizeof(float) * n, stream));
-    sum_cur = 0;
-    for (auto& r : d_ring) CU(cudaMemsetAsync(r.p, 0, sizeof(float) * Y * n, stream));
-    std::vector<float> nd(n, kNoData);
-    CU(cudaMemcpyAsync(d_avg_last.p, nd.data(), sizeof(float) * n, cudaMemcpyHostToDevice, stream));
-    CU(cudaStreamSynchronize(stream));
+    // Stream-ordered and non-blocking: the buffers the NEXT push's K2 reads (m_sum, the current ring) are cleared behind the
+    // kernels already enqueued; the rings / sums older pushes still read (K4's getBestIndex) are not touched.
+    CU(cudaMemsetAsync(d_sum[sum_cur].p, 0, sizeof(float) * n, stream));
+    CU(cudaMemsetAsync(d_ring[ring_cur].p, 0, sizeof(float) * Y * n, stream));
+    k_fill<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(d_avg_last.p, kNoData, static_cast<int>(n));
+    CU(cudaGetLastError());
     avg_frames = 0;
-    ring_cur = 0;
     return 0;
+  }
+  // Transmission::resetBuffers (transmission.cpp:42-55): signals.clear() + Averager::reset(); the noise thresholds stay. Enqueued
+  // behind the pushes already in flight (Scanner hops every 500 ms, scanner.cpp:46-60: a hop must not drain the pipeline).
+  int reset_buffers() {
+    tracker.reset();
+    CU(cudaMemsetAsync(d_state.p, 0, sizeof(TrackState), track_stream));  // behind the K4 of every earlier push, before the next one's
+    {
+      std::lock_guard<std::mutex> lk(qmutex);
+      reset_epoch += 1;  // a chunk enqueued before this moment must not publish its (pre-reset) list afterwards
+      mailbox.clear();
+    }
+    return reset_averager();
   }
 
   // after an overflow: enlarge the per-frame entry lists (no chunk may be in flight)
@@ -621,6 +645,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   const int T = static_cast<int>(frames);
   const size_t bytes_per_sample = cfg.iq_format == B2S_IQ_CS8 ? 2 : 8;
   int rc;
+  s.epoch = reset_epoch;
   s.host_track = out && out->frame_tx_count;  // every frame's list is wanted: the bookkeeping runs on the host (tracker.h)
   if (s.host_track && (rc = state_to_host_tracker())) return rc;
   s.dense_q_on = out && out->noise_sub_db;
@@ -889,12 +914,16 @@ int b2s_band::finish_chunk(PushSlot& s) {
       fprintf(stderr, "[k_track] T=%d cycles %lld: runs %lld eval %lld walk %lld out %lld; evals %d events %d best %d entries %d\n", T, r.cycles, r.phase[0], r.phase[1], r.phase[2],
               r.phase[3], r.n_evals, r.n_events, r.n_best, r.n_entries);
     overflow = worst_count > slot_capacity;
-    mailbox.resize(r.n_tx);
-    std::memcpy(mailbox.data(), r.tx, sizeof(b2s_transmission) * std::min(r.n_tx, B2S_MAX_TX));
+    std::vector<b2s_transmission> list(r.n_tx);
+    std::memcpy(list.data(), r.tx, sizeof(b2s_transmission) * std::min(r.n_tx, B2S_MAX_TX));
     if (r.n_tx > B2S_MAX_TX) {  // rare: the tail of a long list
-      CU(cudaMemcpyAsync(mailbox.data() + B2S_MAX_TX, s.d_result.p->tx + B2S_MAX_TX, sizeof(b2s_transmission) * (r.n_tx - B2S_MAX_TX), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(list.data() + B2S_MAX_TX, s.d_result.p->tx + B2S_MAX_TX, sizeof(b2s_transmission) * (r.n_tx - B2S_MAX_TX), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       prof.d2h_bytes += sizeof(b2s_transmission) * (r.n_tx - B2S_MAX_TX);
+    }
+    {
+      std::lock_guard<std::mutex> lk(qmutex);
+      if (s.epoch == reset_epoch) mailbox.swap(list);  // (a reset issued after this chunk was enqueued has emptied the mailbox: keep it so)
     }
     if (profiling && s.tev[0]) {
       float ms = 0.0f;

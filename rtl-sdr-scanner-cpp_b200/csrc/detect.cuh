@@ -945,6 +945,11 @@ __global__ void k_boxcar_serial(const float* in, float* out, int size, int group
   }
 }
 
+__global__ void k_fill(float* p, float value, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = value;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // self-test: div_const<D> / div_const_fast<D> against IEEE division for every float of the guarded range
 // ------------------------------------------------------------------------------------------------------------

@@ -617,3 +617,50 @@ def test_more_signals_than_the_result_struct_holds(engine):
     assert res.n_transmissions_total == len(want) and res.n_transmissions == b2s.MAX_TX
     assert [(f, fl, k) for f, fl, k, _ in band.get_transmissions()] == want
     assert _mailbox(res) == want[: b2s.MAX_TX]
+
+
+def test_eight_concurrent_bands_with_hops(engine):
+    """BASELINE config 3: eight bands (N = 8192, fs = 2.048 MS/s, one CUDA stream each) in ONE process, pushed asynchronously so
+    their kernels overlap, with Transmission::resetBuffers (the Scanner's hop, scanner.cpp:46-60 / sdr_device.cpp:74) between some
+    pushes and not others. Every band must follow ITS OWN oracle chain: mailbox after every push, signal map, noise, Averager ring."""
+    n, fs, learn, piece, pieces = 8192, 2_048_000, 30, 125, 4
+    period = synth.frame_period_ms(n, fs)  # 4 ms
+    frames = piece * pieces
+    bands, oracles, iqs = [], [], []
+    for b in range(8):
+        tones = [synth.Tone(-3000.1 + 700 * b, amplitude=60.0, fm_dev_bins=6.0, on_frames=[(learn + 20 + 3 * b, learn + 150 + 10 * b), (300 + 5 * b, 460)]),
+                 synth.Tone(1000.1 + 300 * b, amplitude=50.0, fm_dev_bins=5.0, on_frames=[(learn + 60, 280 + 7 * b)], phase=1.0 + b)]
+        iq = synth.make_iq_int8(n, frames, tones, seed=synth.seed_for(3, b), quiet_frames=learn)
+        cfg = b2s.make_config(n, fs, center_hz=int(bench_centres()[b] * 1e6), learn_frames=learn, min_time_ms=80, timeout_ms=120, max_frames_per_push=piece,
+                              flags=b2s.FLAG_ASYNC)
+        ocfg = b2s.make_config(n, fs, center_hz=int(bench_centres()[b] * 1e6), learn_frames=learn, min_time_ms=80, timeout_ms=120)
+        bands.append(b2s.Band(engine, cfg))
+        oracles.append(ol.OracleChain(ocfg))
+        iqs.append(iq)
+    checked = 0
+    for p in range(pieces):
+        t0 = 1000 + int(p * piece * period)
+        for band, iq in zip(bands, iqs):
+            band.push_raw(iq[p * piece * 2 * n :].ctypes.data, piece, t0, period)
+        for b, (band, o, iq) in enumerate(zip(bands, oracles, iqs)):
+            res = band.sync()
+            ref = o.push(iq[p * piece * 2 * n :], piece, t0, period, dense=())
+            assert _mailbox(res) == [(f, fl, k) for f, fl, k, _ in ref.frame_tx[-1]], (p, b)
+            checked += len(ref.frame_tx[-1])
+        if p in (0, 2):  # hop: resetBuffers on every band (not drained first: the reset is ordered behind the pushes in flight)
+            for band, o in zip(bands, oracles):
+                band.reset()
+                o.reset()
+    assert checked > 20
+    for band, o in zip(bands, oracles):
+        for x, y in zip(band.get_signals()[:3], o.get_signals()[:3]):
+            assert np.array_equal(x, y)
+        thr_g, _, ready_g = band.get_noise()
+        thr_o, _, ready_o = o.get_noise()
+        assert ready_g and ready_o and np.max(np.abs(thr_g - thr_o)) <= 2e-3
+
+
+def bench_centres():
+    import bench
+
+    return bench.HOP_CENTRES_MHZ
