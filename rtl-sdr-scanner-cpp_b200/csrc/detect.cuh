@@ -239,6 +239,28 @@ constexpr int kAvgBuffers = B2S_K2_AVG_BUFFERS;  // average tiles between the SU
 static_assert(kAvgBuffers % kBoxGroups == 0 && kAvgBuffers <= 4, "each box group owns whole buffers; barrier ids 2..9");
 constexpr int kBarFull = 2, kBarEmpty = 2 + kAvgBuffers;  // hardware barriers (one pair per average buffer): waiting warps sleep instead of polling
 
+// SPEC warps, one full tile without an emission: out += mean of D adjacent raw bins, frame after frame (spectrogram.cpp:50-58). D is a
+// compile-time constant so that the loads of 8 frames are in flight together; the sum over the D bins runs left to right from 0.0f
+// like the reference's `sum` (0 + x0 is exact), the division by the power of two D is exact as a multiplication.
+template <int D>
+__device__ __forceinline__ float spec_tile(const float* __restrict__ raw, int width, float spec) {
+  constexpr float inv_d = 1.0f / static_cast<float>(D);
+#pragma unroll
+  for (int h = 0; h < kDetectTileFrames; h += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = raw[(h + u) * width];
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __fadd_rn(v[u], raw[(h + u) * width + i]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) spec = __fadd_rn(spec, __fmul_rn(v[u], inv_d));
+  }
+  return spec;
+}
+
 // Y_T / HALF_T: Averager depth and X/2 as compile-time constants (21 / 10 = the reference's GROUPING_Y / GROUPING_X),
 // or 0 / -1 for the generic runtime-parameter instantiation.
 //
@@ -538,15 +560,13 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         const float* __restrict__ raw = psd_tiles + ps * tile_elems + hp + sc * d;
         while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
         const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
-        if (!emits && tf == TF) {
-          float v[TF];
-#pragma unroll
-          for (int f = 0; f < TF; ++f) {
-            v[f] = raw[f * width];
-            for (int i = 1; i < d; ++i) v[f] = __fadd_rn(v[f], raw[f * width + i]);
+        if (!emits && tf == TF && d <= 16) {
+          switch (d) {
+            case 2: spec = spec_tile<2>(raw, width, spec); break;
+            case 4: spec = spec_tile<4>(raw, width, spec); break;
+            case 8: spec = spec_tile<8>(raw, width, spec); break;
+            default: spec = spec_tile<16>(raw, width, spec); break;
           }
-#pragma unroll
-          for (int f = 0; f < TF; ++f) spec = __fadd_rn(spec, __fmul_rn(v[f], inv_d));
         } else {
           for (int f = 0; f < tf; ++f) {
             float v = raw[f * width];
