@@ -204,6 +204,23 @@ int b2s_average(b2s_engine* e, const float* in, float* out, int size, int group_
 /* IQ -> raw PSD rows (unpack, window, FFT, shift, dB) only; power_lin optional (|X|^2/fs) */
 int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_frames, float* psd_db, float* power_lin);
 
+/* ---- recorder chain: what one reference Recorder computes (sources/radio/recorder.cpp:22-40,58-73) ----
+ * rotator_cc(-shift) -> rational_resampler(f1, f2) per pair of getResamplersFactors(fs, bandwidth, RESAMPLER_THRESHOLD = 125)
+ * -> complex_to_interleaved_char(x 127): a continuous IQ stream at fs in, int8 IQ at `bandwidth` samples/s out. The resamplers use
+ * GNU Radio's default taps (Kaiser low-pass, beta 7, fractional bandwidth 0.4); history is zero at b2s_recorder_start.
+ * Chunking into messages (recorder.cpp:35) and the wire format stay host work: b2s_pack_transmission_message. */
+typedef struct b2s_recorder b2s_recorder;
+int b2s_get_resamplers_factors(int32_t sample_rate_hz, int32_t bandwidth_hz, int threshold, int32_t* interp, int32_t* decim, int cap); /* radio_utils.cpp:129-152; returns the count */
+int b2s_recorder_create(b2s_engine* e, int32_t sample_rate_hz, int32_t bandwidth_hz, int iq_format, float iq_scale, int flags /* B2S_FLAG_IQ_ON_DEVICE */,
+                        size_t max_samples_per_push /* 0 -> 4 Mi */, b2s_recorder** out);
+int b2s_recorder_destroy(b2s_recorder* r);
+int b2s_recorder_start(b2s_recorder* r, int32_t shift_hz); /* Recorder::startRecording: rotator phase_inc = 2 pi (-shift) / fs, empty buffers */
+int b2s_recorder_stop(b2s_recorder* r);                    /* Recorder::stopRecording */
+/* n_samples consecutive IQ samples of the stream (host memory, or device memory with B2S_FLAG_IQ_ON_DEVICE) -> *n_out int8 I/Q pairs in out_iq (host) */
+int b2s_recorder_push(b2s_recorder* r, const void* iq, size_t n_samples, int8_t* out_iq, size_t cap_samples, size_t* n_out);
+int b2s_recorder_stages(b2s_recorder* r, int32_t* interp, int32_t* decim, int32_t* n_taps, int cap); /* returns the number of stages */
+int b2s_recorder_taps(b2s_recorder* r, int stage, float* taps, int cap);                            /* returns the number of taps */
+
 /* Self-test: the 3-instruction exact division by a small constant that the Averager (m_sum / GROUPING_Y, averager.cpp:52-60) and
  * boxcar fast paths use, compared with IEEE division for EVERY float with |x| in [2^-60, 2^61) and +-0. *mismatches must be 0. */
 int b2s_selftest_div_const(b2s_engine* e, int divisor, uint64_t* mismatches);

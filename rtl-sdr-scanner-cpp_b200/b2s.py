@@ -557,3 +557,74 @@ def contains_with_margin(keys, index: int, margin: int):
 def most_frequent_value(values) -> int:
     v = np.ascontiguousarray(values, dtype=np.int32)
     return lib().b2s_most_frequent_value(_ptr(v), v.shape[0])
+
+
+def get_resamplers_factors(sample_rate_hz: int, bandwidth_hz: int, threshold: int = 125):
+    """getResamplersFactors (radio_utils.cpp:129-152): [(interpolation, decimation), ...]."""
+    a, b = (C.c_int32 * 16)(), (C.c_int32 * 16)()
+    lib().b2s_get_resamplers_factors.argtypes = [C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    k = lib().b2s_get_resamplers_factors(sample_rate_hz, bandwidth_hz, threshold, a, b, 16)
+    if k < 0:
+        _check(k)
+    return [(a[i], b[i]) for i in range(k)]
+
+
+class Recorder:
+    """The DSP chain of one reference Recorder on the GPU (recorder.cpp:22-40,58-73): rotate by -shift, resample fs -> bandwidth, int8."""
+
+    def __init__(self, engine: Engine, sample_rate_hz: int, bandwidth_hz: int, iq_format: int = IQ_CS8, iq_scale: float = 1.0 / 127.0, on_device: bool = False,
+                 max_samples_per_push: int = 0):
+        L = lib()
+        L.b2s_recorder_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_float, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.b2s_recorder_destroy.argtypes = [C.c_void_p]
+        L.b2s_recorder_start.argtypes = [C.c_void_p, C.c_int32]
+        L.b2s_recorder_stop.argtypes = [C.c_void_p]
+        L.b2s_recorder_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.b2s_recorder_stages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2s_recorder_taps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self._e = engine
+        self.sample_rate_hz, self.bandwidth_hz, self.iq_format = sample_rate_hz, bandwidth_hz, iq_format
+        self._h = C.c_void_p()
+        _check(L.b2s_recorder_create(engine._h, sample_rate_hz, bandwidth_hz, iq_format, iq_scale, FLAG_IQ_ON_DEVICE if on_device else 0, max_samples_per_push, C.byref(self._h)))
+
+    def stages(self):
+        a, b, c = (C.c_int32 * 8)(), (C.c_int32 * 8)(), (C.c_int32 * 8)()
+        k = lib().b2s_recorder_stages(self._h, a, b, c, 8)
+        return [(a[i], b[i], c[i]) for i in range(k)]
+
+    def taps(self, stage: int) -> np.ndarray:
+        n = self.stages()[stage][2]
+        t = np.empty(n, np.float32)
+        assert lib().b2s_recorder_taps(self._h, stage, _ptr(t), n) == n
+        return t
+
+    def start(self, shift_hz: int):
+        _check(lib().b2s_recorder_start(self._h, shift_hz))
+
+    def stop(self):
+        _check(lib().b2s_recorder_stop(self._h))
+
+    def push(self, iq, n_samples: int = None) -> np.ndarray:
+        """iq: numpy array of the stream's next samples (int8 pairs or float32 pairs), or a raw device pointer with n_samples."""
+        if isinstance(iq, np.ndarray):
+            iq = np.ascontiguousarray(iq)
+            n_samples = iq.size // 2
+            ptr = _ptr(iq)
+        else:
+            ptr = C.c_void_p(iq)
+        cap = n_samples * self.bandwidth_hz // self.sample_rate_hz + 64
+        out = np.empty(2 * cap, np.int8)
+        n_out = C.c_size_t()
+        _check(lib().b2s_recorder_push(self._h, ptr, n_samples, _ptr(out), cap, C.byref(n_out)))
+        return out[: 2 * n_out.value]
+
+    def close(self):
+        if self._h:
+            lib().b2s_recorder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -20,6 +20,7 @@
 #include "../../include/b2s.h"
 #include "detect.cuh"
 #include "host_utils.h"
+#include "recorder.cuh"
 #include "spectral3.cuh"
 #include "track.cuh"
 #include "tracker.h"
@@ -381,6 +382,56 @@ static float least_sum_reaching(float level, int divisor) {
 // band
 // ------------------------------------------------------------------------------------------------------------
 #include "band.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// recorder chain (recorder.cuh)
+// ------------------------------------------------------------------------------------------------------------
+// new carry = the last `hc` elements of (old carry ++ fresh[0 .. n_new)); one CTA, read everything before writing anything
+template <typename T>
+__global__ void k_shift_carry(T* carry, const T* fresh, int hc, long long n_new) {
+  extern __shared__ unsigned char carry_smem[];
+  T* tmp = reinterpret_cast<T*>(carry_smem);
+  for (int i = threadIdx.x; i < hc; i += blockDim.x) {
+    const long long j = i + n_new;  // position in (old carry ++ fresh)
+    tmp[i] = j < hc ? carry[j] : fresh[j - hc];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hc; i += blockDim.x) carry[i] = tmp[i];
+}
+
+struct b2s_recorder {
+  b2s_engine* engine = nullptr;
+  int32_t sample_rate = 0, bandwidth = 0;
+  int iq_format = B2S_IQ_CS8;
+  float iq_scale = 1.0f;
+  bool on_device = false, recording = false;
+  size_t max_in = 0;
+  unsigned long long phase_inc = 0;
+  cudaStream_t stream = nullptr;
+  struct Stage {
+    int interp = 1, decim = 1, n_taps = 0, hc = 0;
+    std::vector<float> h_taps;
+    DevBuf<float> taps;
+    DevBuf<float2> buf;      // stages >= 1: [hc carried samples | the previous stage's outputs of this push]
+    long long consumed = 0;  // input samples seen since startRecording
+    long long produced = 0;  // output samples produced since startRecording
+    size_t max_in = 0;
+  };
+  std::vector<Stage> stages;
+  DevBuf<unsigned char> carry_raw, staging;  // stage 0: carried raw samples; host input staging
+  DevBuf<signed char> d_out;
+  ~b2s_recorder() {
+    for (auto& st : stages) {
+      st.taps.release();
+      st.buf.release();
+    }
+    carry_raw.release();
+    staging.release();
+    d_out.release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+  size_t raw_bytes() const { return iq_format == B2S_IQ_CS8 ? 2 : 8; }
+};
 
 // ------------------------------------------------------------------------------------------------------------
 // stand-alone device Averager
@@ -886,6 +937,174 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   dpacked.release();
   if (rc) return rc;
   if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_psd: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+// ---- recorder chain: rotate -> rational resamplers -> int8 (sources/radio/recorder.cpp:22-40,58-73) ----
+int b2s_get_resamplers_factors(int32_t sample_rate_hz, int32_t bandwidth_hz, int threshold, int32_t* interp, int32_t* decim, int cap) {
+  if (sample_rate_hz <= 0 || bandwidth_hz <= 0 || threshold < 1) return fail(B2S_E_INVALID, "b2s_get_resamplers_factors: bad argument");
+  const auto f = host::resamplers_factors(sample_rate_hz, bandwidth_hz, threshold);
+  for (size_t i = 0; i < f.size() && static_cast<int>(i) < cap; ++i) {
+    if (interp) interp[i] = f[i].first;
+    if (decim) decim[i] = f[i].second;
+  }
+  return static_cast<int>(f.size());
+}
+int b2s_recorder_create(b2s_engine* e, int32_t sample_rate_hz, int32_t bandwidth_hz, int iq_format, float iq_scale, int flags, size_t max_samples_per_push, b2s_recorder** out) {
+  if (!e || !out || sample_rate_hz <= 0 || bandwidth_hz <= 0 || bandwidth_hz > sample_rate_hz) return fail(B2S_E_INVALID, "b2s_recorder_create: bad argument");
+  if (iq_format != B2S_IQ_CS8 && iq_format != B2S_IQ_CF32) return fail(B2S_E_INVALID, "unknown iq_format %d", iq_format);
+  *out = nullptr;
+  CU(cudaSetDevice(e->device));
+  auto* r = new b2s_recorder();
+  r->engine = e;
+  r->sample_rate = sample_rate_hz;
+  r->bandwidth = bandwidth_hz;
+  r->iq_format = iq_format;
+  r->iq_scale = iq_scale;
+  r->on_device = (flags & B2S_FLAG_IQ_ON_DEVICE) != 0;
+  r->max_in = max_samples_per_push ? max_samples_per_push : (size_t(1) << 22);
+  int rc = 0;
+  cudaError_t err = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) rc = fail(B2S_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(err));
+  size_t n_in = r->max_in;
+  for (const auto& f : host::resamplers_factors(sample_rate_hz, bandwidth_hz, 125)) {  // RESAMPLER_THRESHOLD, config.h
+    if (rc) break;
+    r->stages.emplace_back();
+    auto& st = r->stages.back();
+    st.interp = f.first;
+    st.decim = f.second;
+    st.h_taps = host::design_resampler_taps(st.interp, st.decim);
+    st.n_taps = static_cast<int>(st.h_taps.size());
+    st.hc = (st.n_taps - 1 + st.decim) / st.interp + 2;
+    st.max_in = n_in;
+    if (st.hc > 4096) rc = fail(B2S_E_INVALID, "resampler stage %d/%d needs %d samples of history", st.interp, st.decim, st.hc);
+    if (!rc) rc = st.taps.alloc(st.n_taps);
+    if (!rc && cudaMemcpy(st.taps.p, st.h_taps.data(), sizeof(float) * st.n_taps, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(B2S_E_CUDA, "taps upload failed");
+    if (!rc && r->stages.size() > 1) rc = st.buf.alloc(st.hc + n_in + 2);
+    n_in = (n_in * st.interp) / st.decim + 2;
+  }
+  if (!rc) rc = r->carry_raw.alloc(static_cast<size_t>(r->stages[0].hc) * r->raw_bytes());
+  if (!rc) rc = r->d_out.alloc(2 * n_in);
+  if (!rc && !r->on_device) rc = r->staging.alloc(r->max_in * r->raw_bytes());
+  if (rc) {
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return 0;
+}
+int b2s_recorder_destroy(b2s_recorder* r) {
+  if (r) {
+    cudaSetDevice(r->engine->device);
+    delete r;
+  }
+  return 0;
+}
+int b2s_recorder_stages(b2s_recorder* r, int32_t* interp, int32_t* decim, int32_t* n_taps, int cap) {
+  if (!r) return fail(B2S_E_INVALID, "NULL recorder");
+  for (size_t i = 0; i < r->stages.size() && static_cast<int>(i) < cap; ++i) {
+    if (interp) interp[i] = r->stages[i].interp;
+    if (decim) decim[i] = r->stages[i].decim;
+    if (n_taps) n_taps[i] = r->stages[i].n_taps;
+  }
+  return static_cast<int>(r->stages.size());
+}
+int b2s_recorder_taps(b2s_recorder* r, int stage, float* taps, int cap) {
+  if (!r || stage < 0 || stage >= static_cast<int>(r->stages.size()) || !taps) return fail(B2S_E_INVALID, "b2s_recorder_taps: bad argument");
+  const auto& h = r->stages[stage].h_taps;
+  std::memcpy(taps, h.data(), sizeof(float) * std::min<size_t>(h.size(), std::max(cap, 0)));
+  return static_cast<int>(h.size());
+}
+// Recorder::startRecording (recorder.cpp:58-73): set the rotator to -shift, start from empty buffers
+int b2s_recorder_start(b2s_recorder* r, int32_t shift_hz) {
+  if (!r) return fail(B2S_E_INVALID, "NULL recorder");
+  // phase increment per sample in turns: -shift / fs, as a 64-bit binary fraction (exact to 2^-65 turns)
+  const long double turns = -static_cast<long double>(shift_hz) / static_cast<long double>(r->sample_rate);
+  long double frac = turns - floorl(turns);  // [0, 1)
+  r->phase_inc = static_cast<unsigned long long>(frac * 18446744073709551616.0L + 0.5L);
+  if (shift_hz != 0 && r->phase_inc == 0) r->phase_inc = 1;
+  for (auto& st : r->stages) st.consumed = st.produced = 0;
+  r->recording = true;
+  return 0;
+}
+int b2s_recorder_stop(b2s_recorder* r) {
+  if (!r) return fail(B2S_E_INVALID, "NULL recorder");
+  r->recording = false;
+  return 0;
+}
+int b2s_recorder_push(b2s_recorder* r, const void* iq, size_t n_samples, int8_t* out_iq, size_t cap_samples, size_t* n_out) {
+  if (!r || (!iq && n_samples) || !n_out) return fail(B2S_E_INVALID, "b2s_recorder_push: NULL argument");
+  *n_out = 0;
+  if (!r->recording) return fail(B2S_E_STATE, "b2s_recorder_push: the recorder is not recording (b2s_recorder_start)");
+  if (n_samples > r->max_in) return fail(B2S_E_INVALID, "b2s_recorder_push: %zu samples exceed max_samples_per_push %zu", n_samples, r->max_in);
+  if (n_samples == 0) return 0;
+  CU(cudaSetDevice(r->engine->device));
+  const void* in = iq;
+  if (!r->on_device) {
+    CU(cudaMemcpyAsync(r->staging.p, iq, n_samples * r->raw_bytes(), cudaMemcpyHostToDevice, r->stream));
+    in = r->staging.p;
+  }
+  long long n_in = static_cast<long long>(n_samples);
+  const void* cur_in = in;
+  const void* cur_carry = r->carry_raw.p;
+  int kind = r->iq_format == B2S_IQ_CS8 ? 0 : 1;
+  long long produced_last = 0;
+  for (size_t si = 0; si < r->stages.size(); ++si) {
+    auto& st = r->stages[si];
+    const bool last = si + 1 == r->stages.size();
+    const long long g0 = st.consumed, g1 = g0 + n_in;
+    const long long m_end = (g1 * st.interp - 1) / st.decim + 1;  // outputs whose newest input has arrived
+    const long long n_new = m_end - st.produced;
+    ResampleArgs a{};
+    a.in = cur_in;
+    a.carry = cur_carry;
+    a.kind = kind;
+    a.iq_scale = r->iq_scale;
+    a.g0 = g0;
+    a.n_in = static_cast<int>(n_in);
+    a.hc = st.hc;
+    a.phase_inc = si == 0 ? r->phase_inc : 0ull;
+    a.taps = st.taps.p;
+    a.n_taps = st.n_taps;
+    a.interp = st.interp;
+    a.decim = st.decim;
+    a.m0 = st.produced;
+    a.n_out = static_cast<int>(n_new);
+    a.per_cta = std::max(1, std::min(kResampleThreads, static_cast<int>((static_cast<long long>(kResampleTile - 2) - st.n_taps / st.interp) * st.interp / st.decim)));
+    float2* next_buf = last ? nullptr : r->stages[si + 1].buf.p;
+    a.out_f = last ? nullptr : next_buf + r->stages[si + 1].hc;
+    a.out_i8 = last ? r->d_out.p : nullptr;
+    if (n_new > 0) {
+      const int grid = static_cast<int>((n_new + a.per_cta - 1) / a.per_cta);
+      k_resample<<<grid, kResampleThreads, sizeof(float2) * kResampleTile, r->stream>>>(a);
+      CU(cudaGetLastError());
+    }
+    // carry the newest inputs of this stage over to the next push
+    if (si == 0) {
+      if (kind == 0) k_shift_carry<short><<<1, 1024, st.hc * 2, r->stream>>>(static_cast<short*>(static_cast<void*>(r->carry_raw.p)), static_cast<const short*>(cur_in), st.hc, n_in);
+      else k_shift_carry<double><<<1, 1024, st.hc * 8, r->stream>>>(static_cast<double*>(static_cast<void*>(r->carry_raw.p)), static_cast<const double*>(cur_in), st.hc, n_in);
+    } else {
+      k_shift_carry<double><<<1, 1024, st.hc * 8, r->stream>>>(reinterpret_cast<double*>(st.buf.p), reinterpret_cast<const double*>(st.buf.p + st.hc), st.hc, n_in);
+    }
+    CU(cudaGetLastError());
+    st.consumed = g1;
+    st.produced = m_end;
+    if (!last) {
+      cur_in = a.out_f;
+      cur_carry = next_buf;
+      kind = 2;
+      n_in = n_new;
+    } else {
+      produced_last = n_new;
+    }
+  }
+  if (static_cast<size_t>(produced_last) > cap_samples) {
+    CU(cudaStreamSynchronize(r->stream));
+    return fail(B2S_E_INVALID, "b2s_recorder_push: %lld output samples, the buffer holds %zu", produced_last, cap_samples);
+  }
+  if (produced_last > 0 && out_iq) CU(cudaMemcpyAsync(out_iq, r->d_out.p, 2 * static_cast<size_t>(produced_last), cudaMemcpyDeviceToHost, r->stream));
+  CU(cudaStreamSynchronize(r->stream));
+  *n_out = static_cast<size_t>(produced_last);
   return 0;
 }
 
