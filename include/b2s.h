@@ -221,6 +221,32 @@ int b2s_recorder_push(b2s_recorder* r, const void* iq, size_t n_samples, int8_t*
 int b2s_recorder_stages(b2s_recorder* r, int32_t* interp, int32_t* decim, int32_t* n_taps, int cap); /* returns the number of stages */
 int b2s_recorder_taps(b2s_recorder* r, int stage, float* taps, int cap);                            /* returns the number of taps */
 
+/* ---- scan policy: Scanner's hop rule and SdrDevice's recorder assignment as a host state machine ----
+ * Scanner::worker (scanner.cpp:36-64): stay on a range while now <= start + RANGE_SCANNING_TIME or the last notification was not
+ * empty. SdrDevice::updateRecordings (sdr_device.cpp:82-144): stop recorders whose shift left the list, flush / start the others.
+ * Ranges are split like Scanner's constructor does (splitRanges(ranges, getRangeSplitSampleRate(fs)), radio_utils.cpp:162-199).
+ * The caller owns the loop: each mailbox list obtained from b2s_band_push / b2s_band_sync is one notification. */
+#define B2S_REC_START 1      /* Recorder::startRecording(frequency, shift) on recorder `recorder` */
+#define B2S_REC_STOP 2       /* Recorder::stopRecording; duration_ms = Recorder::getDuration() */
+#define B2S_REC_FLUSH 3      /* Recorder::flush */
+#define B2S_REC_NONE_FREE 4  /* no recorder available for this shift (logged once, sdr_device.cpp:129-132) */
+typedef struct b2s_recorder_action {
+  int32_t kind;      /* B2S_REC_* */
+  int32_t recorder;  /* index into the pool, -1 for B2S_REC_NONE_FREE */
+  int32_t shift_hz;
+  int64_t duration_ms;
+} b2s_recorder_action;
+typedef struct b2s_scan_policy b2s_scan_policy;
+int b2s_scan_policy_create(const int32_t* range_lo_hz, const int32_t* range_hi_hz, int n_ranges, int32_t sample_rate_hz, int n_recorders, int64_t scanning_time_ms /* 0 -> 500 */,
+                           b2s_scan_policy** out);
+int b2s_scan_policy_destroy(b2s_scan_policy* p);
+int b2s_scan_policy_ranges(b2s_scan_policy* p, int32_t* lo_hz, int32_t* hi_hz, int cap);              /* the split ranges; returns their number */
+int b2s_scan_policy_begin(b2s_scan_policy* p, int64_t now_ms, int32_t* lo_hz, int32_t* hi_hz);          /* first setFrequencyRange */
+/* one notification: recorder actions in the reference's order; *hop != 0 when the scanner retunes, then next_lo/next_hi hold the range */
+int b2s_scan_policy_notify(b2s_scan_policy* p, int64_t now_ms, const b2s_transmission* list, int n, b2s_recorder_action* actions, int cap, int* n_actions, int* hop,
+                           int32_t* next_lo_hz, int32_t* next_hi_hz);
+int32_t b2s_get_range_split_sample_rate(int32_t sample_rate_hz);                                         /* radio_utils.cpp:162-172 */
+
 /* Self-test: the 3-instruction exact division by a small constant that the Averager (m_sum / GROUPING_Y, averager.cpp:52-60) and
  * boxcar fast paths use, compared with IEEE division for EVERY float with |x| in [2^-60, 2^61) and +-0. *mismatches must be 0. */
 int b2s_selftest_div_const(b2s_engine* e, int divisor, uint64_t* mismatches);

@@ -628,3 +628,64 @@ class Recorder:
             self.close()
         except Exception:
             pass
+
+
+class RecorderAction(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("recorder", C.c_int32), ("shift_hz", C.c_int32), ("duration_ms", C.c_int64)]
+
+
+REC_START, REC_STOP, REC_FLUSH, REC_NONE_FREE = 1, 2, 3, 4
+
+
+def get_range_split_sample_rate(sample_rate_hz: int) -> int:
+    lib().b2s_get_range_split_sample_rate.restype = C.c_int32
+    return lib().b2s_get_range_split_sample_rate(sample_rate_hz)
+
+
+class ScanPolicy:
+    """Scanner's hop rule (scanner.cpp:36-64) and SdrDevice::updateRecordings (sdr_device.cpp:82-144) as a host state machine."""
+
+    def __init__(self, ranges, sample_rate_hz: int, n_recorders: int, scanning_time_ms: int = 500):
+        L = lib()
+        L.b2s_scan_policy_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+        L.b2s_scan_policy_destroy.argtypes = [C.c_void_p]
+        L.b2s_scan_policy_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2s_scan_policy_begin.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.b2s_scan_policy_notify.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lo = np.array([r[0] for r in ranges], np.int32)
+        hi = np.array([r[1] for r in ranges], np.int32)
+        self._h = C.c_void_p()
+        _check(L.b2s_scan_policy_create(_ptr(lo), _ptr(hi), len(ranges), sample_rate_hz, n_recorders, scanning_time_ms, C.byref(self._h)))
+
+    def ranges(self):
+        lo, hi = np.zeros(4096, np.int32), np.zeros(4096, np.int32)
+        k = lib().b2s_scan_policy_ranges(self._h, _ptr(lo), _ptr(hi), 4096)
+        return [(int(lo[i]), int(hi[i])) for i in range(k)]
+
+    def begin(self, now_ms: int):
+        lo, hi = C.c_int32(), C.c_int32()
+        _check(lib().b2s_scan_policy_begin(self._h, now_ms, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def notify(self, now_ms: int, transmissions):
+        """transmissions: [(shift_hz, flush), ...] as the mailbox holds them. Returns (actions [(kind, recorder, shift, duration)], next range or None)."""
+        n = len(transmissions)
+        tx = (Transmission * max(n, 1))()
+        for i, (shift, flush) in enumerate(transmissions):
+            tx[i].shift_hz, tx[i].flush = shift, int(flush)
+        acts = (RecorderAction * 256)()
+        na, hop, lo, hi = C.c_int(), C.c_int(), C.c_int32(), C.c_int32()
+        _check(lib().b2s_scan_policy_notify(self._h, now_ms, C.cast(tx, C.c_void_p), n, C.cast(acts, C.c_void_p), 256, C.byref(na), C.byref(hop), C.byref(lo), C.byref(hi)))
+        out = [(acts[i].kind, acts[i].recorder, acts[i].shift_hz, acts[i].duration_ms) for i in range(min(na.value, 256))]
+        return out, ((lo.value, hi.value) if hop.value else None)
+
+    def close(self):
+        if self._h:
+            lib().b2s_scan_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

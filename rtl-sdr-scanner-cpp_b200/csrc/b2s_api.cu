@@ -21,6 +21,7 @@
 #include "detect.cuh"
 #include "host_utils.h"
 #include "recorder.cuh"
+#include "scan_policy.h"
 #include "spectral3.cuh"
 #include "track.cuh"
 #include "tracker.h"
@@ -937,6 +938,54 @@ int b2s_psd(b2s_engine* e, const b2s_band_config* cfg, const void* iq, size_t n_
   dpacked.release();
   if (rc) return rc;
   if (err != cudaSuccess) return fail(B2S_E_CUDA, "b2s_psd: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+// ---- scan policy: Scanner's hop rule + SdrDevice::updateRecordings (scan_policy.h) ----
+struct b2s_scan_policy {
+  host::ScanPolicy policy;
+  b2s_scan_policy(const int32_t* lo, const int32_t* hi, int n, int32_t fs, int rec, int64_t t) : policy(lo, hi, n, fs, rec, t) {}
+};
+int32_t b2s_get_range_split_sample_rate(int32_t sample_rate_hz) { return host::range_split_sample_rate(sample_rate_hz); }
+int b2s_scan_policy_create(const int32_t* lo, const int32_t* hi, int n_ranges, int32_t sample_rate_hz, int n_recorders, int64_t scanning_time_ms, b2s_scan_policy** out) {
+  if (!out || n_ranges < 0 || (n_ranges && (!lo || !hi)) || sample_rate_hz <= 0 || n_recorders < 0) return fail(B2S_E_INVALID, "b2s_scan_policy_create: bad argument");
+  *out = new b2s_scan_policy(lo, hi, n_ranges, sample_rate_hz, n_recorders, scanning_time_ms > 0 ? scanning_time_ms : 500);
+  return 0;
+}
+int b2s_scan_policy_destroy(b2s_scan_policy* p) {
+  delete p;
+  return 0;
+}
+int b2s_scan_policy_ranges(b2s_scan_policy* p, int32_t* lo, int32_t* hi, int cap) {
+  if (!p) return fail(B2S_E_INVALID, "NULL policy");
+  const auto& r = p->policy.ranges;
+  for (size_t i = 0; i < r.size() && static_cast<int>(i) < cap; ++i) {
+    if (lo) lo[i] = r[i].first;
+    if (hi) hi[i] = r[i].second;
+  }
+  return static_cast<int>(r.size());
+}
+int b2s_scan_policy_begin(b2s_scan_policy* p, int64_t now_ms, int32_t* lo, int32_t* hi) {
+  if (!p || p->policy.ranges.empty()) return fail(B2S_E_INVALID, "b2s_scan_policy_begin: no ranges to scan");
+  p->policy.current = 0;
+  p->policy.start = now_ms;
+  if (lo) *lo = p->policy.ranges[0].first;
+  if (hi) *hi = p->policy.ranges[0].second;
+  return 0;
+}
+int b2s_scan_policy_notify(b2s_scan_policy* p, int64_t now_ms, const b2s_transmission* list, int n, b2s_recorder_action* actions, int cap, int* n_actions, int* hop,
+                           int32_t* next_lo, int32_t* next_hi) {
+  if (!p || n < 0 || (n && !list) || !n_actions || !hop) return fail(B2S_E_INVALID, "b2s_scan_policy_notify: bad argument");
+  std::vector<b2s_recorder_action> acts;
+  p->policy.update_recordings(now_ms, list, n, acts);
+  for (size_t i = 0; i < acts.size() && static_cast<int>(i) < cap; ++i) actions[i] = acts[i];
+  *n_actions = static_cast<int>(acts.size());
+  *hop = p->policy.dwell_over(now_ms, n == 0) ? 1 : 0;
+  if (*hop) {
+    p->policy.hop(now_ms);
+    if (next_lo) *next_lo = p->policy.ranges[p->policy.current].first;
+    if (next_hi) *next_hi = p->policy.ranges[p->policy.current].second;
+  }
   return 0;
 }
 
