@@ -188,8 +188,36 @@ def cpu_sample(b2s, synth, ol, wl, iq_segment_fn, threads: int, budget_s: float,
         dt = L.orc_bench_run(C.byref(cfg), iq.ctypes.data_as(C.c_void_p), frames, period, threads)
         runs.append(frames * n / dt / 1e6)
         t_all += dt
+    stages = (C.c_double * 3)()
+    L.orc_bench_stage_seconds(stages)
+    tot = sum(stages) or 1.0
     runs.sort()
-    return {"value": runs[len(runs) // 2], "min": runs[0], "max": runs[-1], "reps": len(runs), "frames": frames}
+    return {"value": runs[len(runs) // 2], "min": runs[0], "max": runs[-1], "reps": len(runs), "frames": frames,
+            "stage_split": {"unpack_window_fft": stages[0] / tot, "psd_db": stages[1] / tot, "noise_averager_detect": stages[2] / tot}}
+
+
+def bind_to_gpu_numa(index: int):
+    """Run this process (and the threads the library starts) on the CPU cores of the NUMA node the GPU hangs off, BEFORE any pinned
+    buffer is allocated (first touch puts the pages there): at 8 GPUs the e2e leg otherwise crosses the socket link for half the
+    GPUs (round 1: 37.5 instead of 52 GB/s per GPU). Returns what was done, for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]  # sysfs uses a 4-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # not fatal: the measurement just runs unbound
+        return {"numa_node": None, "note": f"not bound: {type(e).__name__}"}
 
 
 def fft_backend(ol):
@@ -212,7 +240,7 @@ def run_reference(args, rank, world):
     b2s, synth = ge.load_b2s(), ge.load_synth()
     wl = WORKLOADS[args.config]
     n, fs = wl["n"], wl["fs"]
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     per_thread = max(64, min(512, (1 << 23) // n))
 
     def segment(frames):
@@ -240,7 +268,7 @@ def run_reference(args, rank, world):
         "config": {"workload": wl["name"] + " (CPU arm: bounded sample)", "fft_size": n, "sample_rate_hz": fs, "frames_per_step": frames, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": "MS/s", "cores": cores, "kind": "port", "fft": fft_backend(ol),
                          "spread": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
-                         "single_thread": single["value"],
+                         "single_thread": single["value"], "stage_split_single_thread": single["stage_split"],
                          "sample": f"{frames} frames ({cores} threads x {per_thread} frames, one chain per thread) of the workload per step; restated CPU path, fp32 FFT"},
         "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -281,6 +309,8 @@ def main():
     b2s, synth = ge.load_b2s(), ge.load_synth()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -419,6 +449,33 @@ def main():
             ms_s, agg_s, _, _ = run(Ts, max(args.steps, 5), 3, True)
             sweep.append(summarise(Ts, max(args.steps, 5), ms_s, agg_s))
 
+    # ---- config 4's record leg: rotate + resample 40 MS/s -> 32 kS/s + int8 for the four carriers ----
+    record = None
+    if args.config == 4 and rank == 0:
+        iq4 = synth.make_iq_int8_torch(n, T, tones_for(T), seed=synth.seed_for(4, 0), quiet_frames=LEARN, device=dev)
+        shifts = [b2s.get_tuned_frequency(int(mhz * 1e6), 2500) for mhz in (-12.5, -3.2, 4.7, 15.1)]
+        recs = [b2s.Recorder(eng, fs, 32_000, on_device=True, max_samples_per_push=T * n) for _ in shifts]
+        for r_, sh in zip(recs, shifts):
+            r_.start(sh)
+            r_.push(iq4.data_ptr(), T * n)  # warm-up
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        r0.record(main_stream)
+        out_samples = 0
+        for _ in range(reps):
+            for r_ in recs:
+                out_samples += len(r_.push(iq4.data_ptr(), T * n)) // 2
+        r1.record(main_stream)
+        torch.cuda.synchronize()
+        ms_r = r0.elapsed_time(r1) / reps
+        record = {"recorders": len(recs), "ms_per_step": ms_r, "input_msps_per_recorder": T * n / (ms_r / len(recs) / 1000.0) / 1e6,
+                  "output_samples_per_step": out_samples // reps, "stages": [list(x) for x in recs[0].stages()],
+                  "note": "each recorder reads the step's device-resident IQ (67.1 M samples) once; synchronous pushes, one after the other"}
+        for r_ in recs:
+            r_.close()
+        del iq4
+
     # ---- end-to-end run: pinned host IQ, H2D inside the timed region ----
     e2e = None
     if not args.skip_e2e:
@@ -428,7 +485,7 @@ def main():
             "value": aggregate_msps(samples_step, steps_e, world, ms_e), "unit": "MS/s",
             "h2d_bytes_per_step": int(agg_e["h2d_bytes"] // steps_e), "d2h_bytes_per_step": int(agg_e["d2h_bytes"] // steps_e),
             "steps": steps_e, "ms_per_step": ms_e / steps_e,
-            "pcie_gbs_per_gpu": agg_e["h2d_bytes"] / steps_e / (ms_e / steps_e / 1000.0) / 1e9,
+            "pcie_gbs_per_gpu": agg_e["h2d_bytes"] / steps_e / (ms_e / steps_e / 1000.0) / 1e9, "host_binding": numa,
         }
 
     # ---- cpu baseline (rank 0, N = 1 only): bounded sample of the same workload, all cores and one thread ----
@@ -436,7 +493,8 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         import oracle_lib as ol
 
-        cores = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core, not just the GPU's NUMA node
+        cores = len(all_cpus)
         per_thread = max(64, min(512, (1 << 23) // n))
 
         def segment(frames):
@@ -445,7 +503,7 @@ def main():
         allc = cpu_sample(b2s, synth, ol, wl, segment, cores, 8.0, per_thread)
         one = cpu_sample(b2s, synth, ol, wl, segment, 1, 3.0, per_thread)
         cpu = {"value": allc["value"], "unit": "MS/s", "cores": cores, "kind": "port", "fft": fft_backend(ol),
-               "spread": {"min": allc["min"], "max": allc["max"], "reps": allc["reps"]}, "single_thread": one["value"],
+               "spread": {"min": allc["min"], "max": allc["max"], "reps": allc["reps"]}, "single_thread": one["value"], "stage_split_single_thread": one["stage_split"],
                "sample": f"{allc['reps']} x {allc['frames']} frames ({cores} threads x {per_thread} frames, one chain per thread) of the workload; restated CPU path with fp32 FFT"}
 
     if rank == 0:
@@ -474,6 +532,8 @@ def main():
         }
         if sweep is not None:
             line["sweep"] = sweep
+        if record is not None:
+            line["record_leg"] = record
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

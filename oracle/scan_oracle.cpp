@@ -5,11 +5,15 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <dlfcn.h>
+#include <pthread.h>
+#include <sched.h>
 #include <complex>
 #include <cstring>
 #include <deque>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -215,6 +219,60 @@ struct FftF32 {
   }
 };
 
+// FFTW3f, when the box has it (dlopen: no build-time dependency): the reference's real FFT engine (gr::fft::fft_v plans FFTW3f with
+// FFTW_MEASURE, one thread). Used by the TIMED baseline only — never for parity (its rounding differs from the fp64 oracle's like any
+// fp32 FFT). Absent in the build image; probed at run time so that a box that has libfftw3f.so.3 reports the "FFTW path" row.
+struct Fftw {
+  using plan_t = void*;
+  plan_t (*plan_dft_1d)(int, float (*)[2], float (*)[2], int, unsigned) = nullptr;
+  void (*execute_dft)(plan_t, float (*)[2], float (*)[2]) = nullptr;
+  void (*destroy_plan)(plan_t) = nullptr;
+  void* (*malloc_)(size_t) = nullptr;
+  void (*free_)(void*) = nullptr;
+  bool ok = false;
+  std::mutex planner;  // FFTW's planner is not thread safe
+  Fftw() {
+    void* h = dlopen("libfftw3f.so.3", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libfftw3f.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return;
+    plan_dft_1d = reinterpret_cast<decltype(plan_dft_1d)>(dlsym(h, "fftwf_plan_dft_1d"));
+    execute_dft = reinterpret_cast<decltype(execute_dft)>(dlsym(h, "fftwf_execute_dft"));
+    destroy_plan = reinterpret_cast<decltype(destroy_plan)>(dlsym(h, "fftwf_destroy_plan"));
+    malloc_ = reinterpret_cast<decltype(malloc_)>(dlsym(h, "fftwf_malloc"));
+    free_ = reinterpret_cast<decltype(free_)>(dlsym(h, "fftwf_free"));
+    ok = plan_dft_1d && execute_dft && destroy_plan && malloc_ && free_;
+  }
+  static Fftw& get() {
+    static Fftw f;
+    return f;
+  }
+};
+struct FftwPlan {
+  Fftw::plan_t plan = nullptr;
+  float (*buf)[2] = nullptr;
+  int n = 0;
+  explicit FftwPlan(int size) : n(size) {
+    Fftw& f = Fftw::get();
+    if (!f.ok) return;
+    std::lock_guard<std::mutex> lk(f.planner);
+    buf = static_cast<float (*)[2]>(f.malloc_(sizeof(float) * 2 * n));
+    if (buf) plan = f.plan_dft_1d(n, buf, buf, -1 /* FFTW_FORWARD */, 0u /* FFTW_MEASURE */);
+  }
+  ~FftwPlan() {
+    Fftw& f = Fftw::get();
+    if (!f.ok) return;
+    std::lock_guard<std::mutex> lk(f.planner);
+    if (plan) f.destroy_plan(plan);
+    if (buf) f.free_(buf);
+  }
+  bool usable() const { return plan != nullptr; }
+  void run(std::complex<float>* x) const {  // in place through the aligned planning buffer
+    std::memcpy(buf, static_cast<const void*>(x), sizeof(float) * 2 * n);
+    Fftw::get().execute_dft(plan, buf, buf);
+    std::memcpy(static_cast<void*>(x), buf, sizeof(float) * 2 * n);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Averager — sources/radio/averager.cpp:7-60 (state must be bit-exact)
 // ---------------------------------------------------------------------------------------------------------------
@@ -302,6 +360,9 @@ struct orc_chain {
   std::vector<float> window;
   FftPlan<double> plan64;
   FftF32 plan32;
+  FftwPlan planw;  // the timed baseline prefers FFTW3f when the box has it
+  double stageSeconds[3] = {0.0, 0.0, 0.0};  // timed baseline only: unpack+window+FFT, PSD, noise+averager+detect(+spectrogram)
+  bool timeStages = false;
   std::map<int32_t, NoiseState> noise;  // keyed by centre frequency, noise_learner.cpp:41-42
   RingAverager averager;
   std::map<int, TrackedSignal> signals;  // transmission.h:49
@@ -318,6 +379,7 @@ struct orc_chain {
         window(c.fft_size),
         plan64(c.fft_size),
         plan32(c.fft_size),
+        planw(c.fft_size),
         averager(c.fft_size, c.grouping_y),
         center(c.center_hz),
         rangeLo(c.range_lo_hz),
@@ -355,6 +417,7 @@ struct orc_chain {
   void framePsd(const void* iqFrame, float* out, float* lin) {
     const int n = cfg.fft_size;
     const bool f32 = (cfg.flags & 1) != 0;
+    const auto ts0 = timeStages ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
     for (int i = 0; i < n; ++i) {
       float re, im;
       if (cfg.iq_format == 0) {  // CS8; the unpack lives in the SoapySDR driver in the reference (sdr_source.cpp:52)
@@ -376,10 +439,11 @@ struct orc_chain {
       }
     }
     if (f32) {
-      plan32.run(work32.data());
+      if (planw.usable()) planw.run(work32.data()); else plan32.run(work32.data());
     } else {
       plan64.run(work64.data());
     }
+    const auto ts1 = timeStages ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
     const float fs = static_cast<float>(cfg.sample_rate_hz);  // int32 promoted to float in psd.cpp:19
     for (int j = 0; j < n; ++j) {
       const int k = (j + n / 2) % n;  // fft_v shift=true: out[j] = X[(j + N/2) mod N]
@@ -390,6 +454,11 @@ struct orc_chain {
         z = std::complex<float>(static_cast<float>(work64[k].real()), static_cast<float>(work64[k].imag()));
       }
       out[j] = psdDb(z, fs, lin ? &lin[j] : nullptr);
+    }
+    if (timeStages) {
+      const auto ts2 = std::chrono::steady_clock::now();
+      stageSeconds[0] += std::chrono::duration<double>(ts1 - ts0).count();
+      stageSeconds[1] += std::chrono::duration<double>(ts2 - ts1).count();
     }
   }
 
@@ -505,6 +574,7 @@ struct orc_chain {
         const char* frame = static_cast<const char*>(iq) + k * static_cast<size_t>(cfg.frame_stride_samples) * bytesPerSample;
         framePsd(frame, psd.data(), nullptr);
       }
+      const auto td0 = timeStages ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
       if (out && out->psd_db) std::memcpy(out->psd_db + k * n, psd.data(), sizeof(float) * n);
       spectrogram(psd.data(), now);  // wired to the raw PSD, sdr_device.cpp:170-171
 
@@ -524,6 +594,7 @@ struct orc_chain {
       if (out && out->noise_sub_db) std::memcpy(out->noise_sub_db + k * n, sub.data(), sizeof(float) * n);
       if (out && out->peak_index) out->peak_index[k] = peak;
       detect(sub.data(), now, static_cast<int>(k), out);
+      if (timeStages) stageSeconds[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
     }
     return 0;
   }
@@ -712,13 +783,35 @@ void orc_averager_data(orc_averager* a, float* out) {
 void orc_averager_sum(orc_averager* a, float* out) { std::memcpy(out, a->impl.sum.data(), sizeof(float) * a->impl.size); }
 int orc_averager_frames(orc_averager* a) { return a->impl.frames; }
 
+// stage split of the most recent orc_bench_run, summed over its threads: [0] unpack+window+FFT, [1] PSD (hypot/pow/log10), [2] noise +
+// Averager + boxcar + detection + spectrogram
+static double g_stage_seconds[3] = {0.0, 0.0, 0.0};
+void orc_bench_stage_seconds(double* out) {
+  for (int i = 0; i < 3; ++i) out[i] = g_stage_seconds[i];
+}
+const char* orc_fft_backend() { return Fftw::get().ok ? "FFTW3f (dlopen libfftw3f.so.3, FFTW_MEASURE, 1 thread per chain)" : "in-repo fp32 radix-4 Stockham (FFTW3f not on this box)"; }
+
 double orc_bench_run(const orc_config* cfg, const void* iq, size_t nFrames, double period, int threads) {
   if (threads < 1) threads = 1;
   orc_config c = *cfg;
   c.flags |= 1;  // fp32 FFT: the timed baseline
   const size_t bytesPerSample = c.iq_format == 0 ? 2 : 8;
   std::vector<orc_chain*> chains;
-  for (int t = 0; t < threads; ++t) chains.push_back(new orc_chain(c));
+  for (int t = 0; t < threads; ++t) {
+    chains.push_back(new orc_chain(c));
+    chains.back()->timeStages = true;
+  }
+  // one chain per thread, each thread pinned to its own core of the process's affinity mask (reproducible across boxes)
+  std::vector<int> cpus;
+  {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+      for (int i = 0; i < CPU_SETSIZE; ++i) {
+        if (CPU_ISSET(i, &set)) cpus.push_back(i);
+      }
+    }
+  }
   const size_t per = nFrames / threads;
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
@@ -726,6 +819,12 @@ double orc_bench_run(const orc_config* cfg, const void* iq, size_t nFrames, doub
     const size_t begin = per * t;
     const size_t count = (t == threads - 1) ? nFrames - begin : per;
     pool.emplace_back([&, t, begin, count]() {
+      if (!cpus.empty()) {
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(cpus[t % cpus.size()], &one);
+        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      }
       const char* base = static_cast<const char*>(iq) + begin * static_cast<size_t>(c.frame_stride_samples) * bytesPerSample;
       orc_outputs out{};
       std::vector<int32_t> cnt(count), freq(count * ORC_MAX_TX), fl(count * ORC_MAX_TX);
@@ -737,7 +836,11 @@ double orc_bench_run(const orc_config* cfg, const void* iq, size_t nFrames, doub
   }
   for (auto& th : pool) th.join();
   const auto t1 = std::chrono::steady_clock::now();
-  for (auto* ch : chains) delete ch;
+  for (int i = 0; i < 3; ++i) g_stage_seconds[i] = 0.0;
+  for (auto* ch : chains) {
+    for (int i = 0; i < 3; ++i) g_stage_seconds[i] += ch->stageSeconds[i];
+    delete ch;
+  }
   return std::chrono::duration<double>(t1 - t0).count();
 }
 }

@@ -125,6 +125,8 @@ int orc_averager_frames(orc_averager* a);
 /* multi-threaded throughput run of the fp32 path for bench.py (cpu_baseline / --impl reference):
  * splits n_frames into `threads` contiguous segments, each with its own chain. Returns seconds. */
 double orc_bench_run(const orc_config* cfg, const void* iq, size_t n_frames, double frame_period_ms, int threads);
+void orc_bench_stage_seconds(double* out3); /* of the last run, summed over threads: unpack+window+FFT, PSD, noise+averager+detect */
+const char* orc_fft_backend(void);           /* FFTW3f when the box has libfftw3f.so.3 (probed with dlopen), else the in-repo fp32 FFT */
 
 #ifdef __cplusplus
 }
