@@ -82,6 +82,7 @@ struct DetectArgs {
   int* cand_flag;            // [T] set to 1 when an uncovered candidate exists
   // rows to emit during this push, planned by the host from the frame clock (Spectrogram::send, spectrogram.cpp:62-75).
   // Carried in the kernel arguments so that no small host->device copy sits on the critical path behind the bulk IQ copy.
+  unsigned int emit_tiles[8];      // bit t: a row is emitted inside tile t of the push (max_frames <= 8192; beyond that every tile is checked)
   int n_emit;                      // <= kMaxSpecEmits
   int emit_frame[kMaxSpecEmits];   // frame after which row i is emitted (ascending)
   int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
@@ -263,6 +264,9 @@ static_assert(kDetectBinsPerCta / 2 <= kSpecThreads, "one SPEC thread per spectr
 #ifndef B2S_K2_CPASYNC
 #define B2S_K2_CPASYNC 0  // PSD tiles through one 2-D TMA load per tile (0) or 16-byte cp.async chunks (1: measured slower, 0.265 vs 0.135 ms per CTA)
 #endif
+#ifndef B2S_K2_DIAG
+#define B2S_K2_DIAG 0  // timing diagnostics only (wrong results): 1 = box warps skip the division and the boxcar, 2 = SUM warps skip the march
+#endif
 #ifndef B2S_K2_EARLY_EMPTY
 #define B2S_K2_EARLY_EMPTY 1
 #endif
@@ -411,13 +415,19 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       if (tile >= kAvgBuffers) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this average buffer
       float q[TF];
       float checkpoint = 0.0f;
-      bool emits = false;  // a spectrogram row completes inside this tile
-      if (next_emit < a.n_emit) {
+      // a spectrogram row completes inside this tile: one bit per tile, set by the host (a scan of the emission table with its
+      // indexed constant loads sat on the serial chain's warps every tile)
+      const bool emits = tile < 256 ? ((a.emit_tiles[tile >> 5] >> (tile & 31)) & 1u) != 0u : a.n_emit > 0;
+      if (emits) {
         while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-        emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
       }
       const bool spec_inline = steady && d == 1 && !emits;
+#if B2S_K2_DIAG == 2
       if (steady) {
+      } else if (false) {
+#else
+      if (steady) {
+#endif
         if (active) {
           checkpoint = sum;  // m_sum before frame t0
           // two halves: the second half of the tile is loaded only when most of `lead` is dead, which keeps the live set at
@@ -487,7 +497,8 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         }
       }
       if (ct == 0) tile_raw[sb] = steady ? 1 : 0;
-      __threadfence_block();
+      // (no fence: the barrier instruction orders this warp's shared-memory stores before the waiting warps' loads — the
+      // producer / consumer pattern of the PTX manual; MEMBAR.SC.CTA here also waited for the warp's global stores)
       bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of averages to the box warps
       if (spec_owner && !spec_inline) {  // tiles with an emission, non-steady tiles
         const float* __restrict__ raw = cur;
@@ -593,8 +604,10 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       mbar_wait_sleepy(&p_full[ps], ps_phase);
       if (on) {
         const float* __restrict__ raw = psd_tiles + ps * tile_elems + hp + sc * d;
-        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-        const bool emits = next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + tf;
+        const bool emits = tile < 256 ? ((a.emit_tiles[tile >> 5] >> (tile & 31)) & 1u) != 0u : a.n_emit > 0;
+        if (emits) {
+          while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
+        }
         if (!emits && tf == TF && d <= 16) {
           switch (d) {
             case 2: spec = spec_tile<2>(raw, width, spec); break;
@@ -657,7 +670,11 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           float w[SEG + 2 * H];
 #pragma unroll
           for (int i = 0; i < SEG + 2 * H; ++i) w[i] = avg_tile[(hp + b0 - H + i) * kSumPitch + f];  // columns outside [0, N) hold 0.0f
+#if B2S_K2_DIAG == 1
+          if (false) {
+#else
           if (raw) {
+#endif
 #pragma unroll
             for (int i = 0; i < SEG + 2 * H; ++i) w[i] = div_const_fast<YD>(w[i]);  // averager.cpp:52-60 (0 / Y = 0 for the zero extension)
 #if B2S_K2_EARLY_EMPTY
@@ -667,7 +684,12 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
             released = true;
 #endif
           }
+#if B2S_K2_DIAG == 1
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) box[k] = w[k + H];
+#else
           boxcar_segment<H>(w, box);
+#endif
           if (segment_interior(bin0, n, half)) {
             scaled = !a.dense_box;
             if (!scaled) {
