@@ -764,6 +764,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.spec_rows = s.spec_rows.p;
   da.box_last = s.host_track ? nullptr : s.box_last.p;
   da.cta_ns = nullptr;
+  da.trace_cta = -1;
+  if (const char* e = getenv("B2S_K2_TRACE_CTA")) da.trace_cta = atoi(e);
   if (profiling && profile_ctas) {
     if ((rc = s.cta_ns.alloc(2 * ((n + detect_bins - 1) / detect_bins)))) return rc;
     da.cta_ns = s.cta_ns.p;

@@ -88,6 +88,7 @@ struct DetectArgs {
   int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
   signed char* spec_rows;          // [n_emit][M]
   unsigned long long* cta_ns;      // optional [2 * grid]: %globaltimer at CTA start / end (profiling: load balance)
+  int trace_cta;                   // >= 0: this CTA prints where its SUM warp 0 and box warp (group 0, segment 0) spend their cycles
   float* box_last;  // optional [N]: the boxcar row of the push's last frame (K4 reads the signals' m_power from it)
   // optional dense rows [T][N]
   float* dense_q;
@@ -404,6 +405,9 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
 
     int ps = 0;            // PSD ring slot of the current tile and the parity of its mbarrier phase
     uint32_t ps_phase = 0;
+    const bool tr = a.trace_cta == static_cast<int>(blockIdx.x) && ct == 0;
+    long long tr_c[4] = {0, 0, 0, 0};
+    const long long tr_begin = tr ? clock64() : 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
@@ -411,8 +415,11 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       const float* __restrict__ cur = psd_tiles + ps * tile_elems + ct;
       float* __restrict__ sum_col = sum_tiles + sb * sum_elems + ct * kSumPitch;  // my column of the transposed tile
       const bool steady = tile >= first_steady && tf == TF;  // the previous tile was full, so `lead` is valid
+      const long long c0 = tr ? clock64() : 0;
       mbar_wait_sleepy(&p_full[ps], ps_phase);                              // the PSD tile has landed
+      const long long c1 = tr ? clock64() : 0;
       if (tile >= kAvgBuffers) bar_sync(kBarEmpty + sb, kSumThreads + kBoxThreads);  // the box warps are done with this average buffer
+      const long long c2 = tr ? clock64() : 0;
       float q[TF];
       float checkpoint = 0.0f;
       // a spectrogram row completes inside this tile: one bit per tile, set by the host (a scan of the emission table with its
@@ -499,7 +506,13 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       if (ct == 0) tile_raw[sb] = steady ? 1 : 0;
       // (no fence: the barrier instruction orders this warp's shared-memory stores before the waiting warps' loads — the
       // producer / consumer pattern of the PTX manual; MEMBAR.SC.CTA here also waited for the warp's global stores)
+      const long long c3 = tr ? clock64() : 0;
       bar_arrive(kBarFull + sb, kSumThreads + kBoxThreads);  // hand the tile of averages to the box warps
+      if (tr) {
+        tr_c[0] += c1 - c0;
+        tr_c[1] += c2 - c1;
+        tr_c[2] += c3 - c2;
+      }
       if (spec_owner && !spec_inline) {  // tiles with an emission, non-steady tiles
         const float* __restrict__ raw = cur;
         for (int f = 0; f < tf; ++f) {
@@ -526,6 +539,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         for (int f = 0; f < YC; ++f) lead[f] = q[TF - YC + f];
       }
     }
+    if (tr) printf("[k_detect cta %d] SUM warp 0: total %lld cycles: wait tile %lld, wait EMPTY %lld, march %lld, rest %lld (%d tiles)\n", blockIdx.x, clock64() - tr_begin, tr_c[0], tr_c[1], tr_c[2], clock64() - tr_begin - tr_c[0] - tr_c[1] - tr_c[2], n_tiles);
     if (spec_owner) a.spec_sum[j] = spec;
     if (owner) {
       a.threshold_out[j] = thr;
@@ -648,11 +662,15 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     const int b0 = seg * SEG, bin0 = j0 + b0;
     float* my_box = box_park + (group * kBoxWarps + seg) * SEG * TF + lane;  // [k * TF]: written and read by this lane only
     static_assert(kBoxGroups == 1 || kBoxGroups == 2, "group g takes the tiles with tile % kBoxGroups == g");
+    const bool btr = a.trace_cta == static_cast<int>(blockIdx.x) && group == 0 && btid == 0;
+    long long btr_c[3] = {0, 0, 0};
     for (int tile = group; tile < n_tiles; tile += kBoxGroups) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
       const int sb = tile % kAvgBuffers;
+      const long long b0c = btr ? clock64() : 0;
       bar_sync(kBarFull + sb, kSumThreads + kBoxThreads);  // the SUM warps have written this tile
+      const long long b1c = btr ? clock64() : 0;
       const float* avg_tile = sum_tiles + sb * sum_elems;
       const bool raw = tile_raw[sb] != 0;  // the SUM warps handed over m_sum: m_average = m_sum / Y is computed here
       const int f = lane, t = t0 + f;
@@ -710,6 +728,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         }
       }
       if (!released && tile + kAvgBuffers < n_tiles) bar_arrive(kBarEmpty + sb, kSumThreads + kBoxThreads);  // this average buffer may be overwritten
+      const long long b2c = btr ? clock64() : 0;
       constexpr int XD = HALF_T > 0 ? 2 * HALF_T + 1 : 1;
       auto value_of = [&](float b) { return scaled ? div_const_fast<XD>(b) : b; };  // average(avg, X)[bin], utils.cpp:49
       const float lvl_detect = scaled ? a.detect_sum : a.detect_level, lvl_start = scaled ? a.start_sum : a.start_level;
@@ -778,7 +797,14 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           ++pos;
         }
       }
+      if (btr) {
+        const long long b3c = clock64();
+        btr_c[0] += b1c - b0c;
+        btr_c[1] += b2c - b1c;
+        btr_c[2] += b3c - b2c;
+      }
     }
+    if (btr) printf("[k_detect cta %d] box warp g0 s0: wait FULL %lld, load+div+boxcar %lld, entries+rest %lld\n", blockIdx.x, btr_c[0], btr_c[1], btr_c[2]);
     if (a.cta_ns && btid == 0 && group == (n_tiles - 1) % kBoxGroups) a.cta_ns[2 * blockIdx.x + 1] = global_timer_ns();
   }
 }
