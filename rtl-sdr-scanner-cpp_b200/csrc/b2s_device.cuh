@@ -82,6 +82,67 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x)); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ float2 cneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 cmake(float2, float re, float im) { return make_float2(re, im); }  // (tag, re, im): construct a value of the tag's type
+// acc + a * w with the reference-free but fixed operation order of the split pre-pass (spectral3.cuh)
+__device__ __forceinline__ float2 cmadd(float2 a, float2 w, float2 acc) {
+  return make_float2(fmaf(a.x, w.x, fmaf(-a.y, w.y, acc.x)), fmaf(a.x, w.y, fmaf(a.y, w.x, acc.y)));
+}
+__device__ __forceinline__ float cre(float2 a) { return a.x; }
+__device__ __forceinline__ float cim(float2 a) { return a.y; }
+
+// ---------------------------------------------------------------------------------------------------------
+// packed complex: one 64-bit register pair (re = low half, im = high half) driven through Blackwell's two-wide fp32
+// instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2). ptxas folds the half swap (LO_HI), the per-half
+// negation (.NP / .PN) and the broadcast of a scalar or an immediate (.F32) into the operand modifiers of those instructions,
+// so a complex add, a multiplication by -i fused into the following add, and a scaling are ONE instruction each and a
+// complex multiplication is TWO (scalar code: 2 / 2 / 2 / 4). Every half is computed with the IEEE round-to-nearest
+// operation of the scalar form (add, sub, mul, fma), so results differ from the float2 helpers above only where a complex
+// product rounds its two partial products in the other order.
+// ---------------------------------------------------------------------------------------------------------
+struct __align__(8) cpk {
+  float x, y;
+};
+__device__ __forceinline__ cpk cpk_make(float re, float im) {
+  cpk r;
+  r.x = re;
+  r.y = im;
+  return r;
+}
+__device__ __forceinline__ float cre(cpk a) { return a.x; }
+__device__ __forceinline__ float cim(cpk a) { return a.y; }
+__device__ __forceinline__ cpk cmake(cpk, float re, float im) { return cpk_make(re, im); }
+#define B2S_F32X2_OP2(name, op)                                                                                   \
+  __device__ __forceinline__ cpk name(cpk a, cpk b) {                                                             \
+    cpk r;                                                                                                        \
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" op " rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}" \
+        : "=f"(r.x), "=f"(r.y)                                                                                    \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                                \
+    return r;                                                                                                     \
+  }
+B2S_F32X2_OP2(cadd, "add.rn.f32x2")
+B2S_F32X2_OP2(csub, "sub.rn.f32x2")
+B2S_F32X2_OP2(cpk_mul2, "mul.rn.f32x2")  // per half
+#undef B2S_F32X2_OP2
+__device__ __forceinline__ cpk cpk_fma2(cpk a, cpk b, cpk c) {  // per half
+  cpk r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\tfma.rn.f32x2 rr, ra, rb, rc;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ cpk mul_mi(cpk a) { return cpk_make(cim(a), -cre(a)); }  // a * (-i): folded into the consumer's operand modifiers
+__device__ __forceinline__ cpk cneg(cpk a) { return cpk_make(-cre(a), -cim(a)); }
+__device__ __forceinline__ cpk cscale(cpk a, float s) { return cpk_mul2(a, cpk_make(s, s)); }
+__device__ __forceinline__ cpk cmul(cpk a, float2 w) {  // (a.x w.x - a.y w.y, a.y w.x + a.x w.y)
+  const cpk t = cpk_mul2(a, cpk_make(w.x, w.x));
+  return cpk_fma2(cpk_make(-cim(a), cre(a)), cpk_make(w.y, w.y), t);
+}
+__device__ __forceinline__ cpk cmadd(cpk a, float2 w, cpk acc) {  // acc + a * w
+  const cpk t = cpk_fma2(cpk_make(-cim(a), cre(a)), cpk_make(w.y, w.y), acc);
+  return cpk_fma2(a, cpk_make(w.x, w.x), t);
+}
 
 // first-maximum argmax reduction (ties -> lower index), matching the strict '<' scan of noise_learner.cpp:53-59
 __device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {

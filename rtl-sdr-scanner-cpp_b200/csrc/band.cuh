@@ -393,7 +393,7 @@ struct b2s_band : public DeviceQueries {
       if ((rc = r.alloc(Y * n))) return rc;
     }
     if ((rc = d_avg_last.alloc(n))) return rc;
-    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * slot_capacity))) return rc;
+    if ((rc = d_slots.alloc(static_cast<size_t>((max_frames + 31) & ~31) * slot_capacity))) return rc;
     if ((rc = d_slot_count.alloc(max_frames))) return rc;
     rc = reset_averager();
     if (rc) return rc;
@@ -529,7 +529,7 @@ struct b2s_band : public DeviceQueries {
     for (int i = 0; i < n_slots; ++i) {
       if ((rc = slots[i].sorted.alloc(static_cast<size_t>(max_frames) * cap))) return rc;
     }
-    if ((rc = d_slots.alloc(static_cast<size_t>(max_frames) * cap))) return rc;
+    if ((rc = d_slots.alloc(static_cast<size_t>((max_frames + 31) & ~31) * cap))) return rc;
     slot_capacity = cap;
     return 0;
   }
@@ -766,6 +766,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.cta_ns = nullptr;
   da.trace_cta = -1;
   if (const char* e = getenv("B2S_K2_TRACE_CTA")) da.trace_cta = atoi(e);
+  if (const char* e = getenv("B2S_K2_TRACE_SEG")) da.trace_seg = atoi(e);
   if (profiling && profile_ctas) {
     if ((rc = s.cta_ns.alloc(2 * ((n + detect_bins - 1) / detect_bins)))) return rc;
     da.cta_ns = s.cta_ns.p;
@@ -987,6 +988,13 @@ int b2s_band::finish_chunk(PushSlot& s) {
       CU(cudaStreamSynchronize(st));
       std::vector<double> dur(grid);
       for (int i = 0; i < grid; ++i) dur[i] = static_cast<double>(ns[2 * i + 1] - ns[2 * i]) * 1e-6;
+      if (getenv("B2S_K2_DUMP_CTAS")) {  // diagnostics: start (relative to the first CTA) and run time of every CTA, in microseconds
+        unsigned long long first = ~0ull;
+        for (int i = 0; i < grid; ++i) first = std::min(first, ns[2 * i]);
+        fprintf(stderr, "[k_detect ctas]");
+        for (int i = 0; i < grid; ++i) fprintf(stderr, " %d:%.1f+%.1f", i, static_cast<double>(ns[2 * i] - first) * 1e-3, dur[i] * 1e3);
+        fprintf(stderr, "\n");
+      }
       std::sort(dur.begin(), dur.end());
       prof.detect_cta_median_ms += dur[grid / 2];
       prof.detect_cta_max_ms += dur[grid - 1];

@@ -29,10 +29,18 @@ constexpr int kMaxSpecEmits = 16;       // spectrogram rows that one push (chunk
 constexpr int kMaxWatch = 16;           // live signal keys whose window maxima K2 reports directly
 constexpr int kCheckpointEvery = 64;    // frames between Averager-sum checkpoints (replay points for K3)
 
-struct DetectEntry {  // one bin whose boxcar power reached min(start, stop) in one frame
+struct __align__(8) DetectEntry {  // one bin whose boxcar power reached min(start, stop) in one frame (8-byte aligned: ONE 8-byte store per entry)
   int bin;
   float value;  // boxcar-averaged power (dB above learned noise)
 };
+// Slot lists in memory: entry `pos` of frame t lives at ((t / 32) * capacity + pos) * 32 + t % 32 — the 32 frames of a K2 tile are the
+// minor index. A box warp's lanes are the 32 frames of a tile, and lanes with equal list positions then write adjacent 8-byte
+// cells: a warp-wide store touches 2 cache lines instead of 32. (Measured with frame-major lists [t][capacity]: every store of
+// the CTA that carries an emitter's core took 32 L1 tag cycles, 110 k cycles per push, and the whole CTA — its SUM warps'
+// shared-memory traffic queues behind them — ran 40 % longer than its neighbours; the kernel ends with its slowest CTA.)
+__host__ __device__ __forceinline__ size_t slot_index(int t, int pos, int capacity) {
+  return (static_cast<size_t>(t >> 5) * capacity + pos) * 32 + (t & 31);
+}
 
 struct DetectArgs {
   // geometry
@@ -64,7 +72,7 @@ struct DetectArgs {
   // the same two levels as thresholds on the UNDIVIDED boxcar sum of an interior bin: x >= detect_sum  <=>  x / X >= detect_level
   // (IEEE division is monotonic, so the set {x : fl(x / X) >= level} is an upper interval; the host finds its least element)
   float detect_sum, start_sum;
-  DetectEntry* slots;     // [T][slot_capacity]
+  DetectEntry* slots;     // [ceil(T/32)][slot_capacity][32], see slot_index()
   int* slot_count;        // [T] (zeroed before launch); may exceed slot_capacity -> overflow, reported by the host
   int slot_capacity;
   // spectrogram
@@ -88,7 +96,7 @@ struct DetectArgs {
   int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
   signed char* spec_rows;          // [n_emit][M]
   unsigned long long* cta_ns;      // optional [2 * grid]: %globaltimer at CTA start / end (profiling: load balance)
-  int trace_cta;                   // >= 0: this CTA prints where its SUM warp 0 and box warp (group 0, segment 0) spend their cycles
+  int trace_cta, trace_seg;        // trace_cta >= 0: this CTA prints where its SUM warp 0 and box warp (group 0, segment trace_seg) spend their cycles
   float* box_last;  // optional [N]: the boxcar row of the push's last frame (K4 reads the signals' m_power from it)
   // optional dense rows [T][N]
   float* dense_q;
@@ -662,7 +670,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     const int b0 = seg * SEG, bin0 = j0 + b0;
     float* my_box = box_park + (group * kBoxWarps + seg) * SEG * TF + lane;  // [k * TF]: written and read by this lane only
     static_assert(kBoxGroups == 1 || kBoxGroups == 2, "group g takes the tiles with tile % kBoxGroups == g");
-    const bool btr = a.trace_cta == static_cast<int>(blockIdx.x) && group == 0 && btid == 0;
+    const bool btr = a.trace_cta == static_cast<int>(blockIdx.x) && group == 0 && btid == 32 * a.trace_seg;
     long long btr_c[3] = {0, 0, 0};
     for (int tile = group; tile < n_tiles; tile += kBoxGroups) {
       const int t0 = tile * TF;
@@ -753,11 +761,21 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
             if (bin0 + k < n) a.box_last[bin0 + k] = value_of(box[k]);
         }
         if (top >= lvl_detect) {
+          // A segment inside an emitter's skirt has all 16 bins at or above the level (the benchmark scene: ~260 bins per carrier):
+          // that case is decided with 8 three-input minima and written out from registers below, without the mask, the parking
+          // and the bit loop (the box warps of a CTA that carries an emitter take issue slots from its SUM warps).
+          float bot = box[0];
 #pragma unroll
-          for (int k = 0; k < SEG; ++k) hits |= (bin0 + k < n && box[k] >= lvl_detect) ? (1u << k) : 0u;
+          for (int k = 1; k < SEG; ++k) bot = fminf(bot, box[k]);
+          if (bot >= lvl_detect && bin0 + SEG <= n) {
+            hits = (1u << SEG) - 1u;
+          } else {
 #pragma unroll
-          for (int k = 0; k < SEG; ++k) my_box[k * TF] = box[k];  // parked: the write-out below indexes them dynamically
-          parked = true;
+            for (int k = 0; k < SEG; ++k) hits |= (bin0 + k < n && box[k] >= lvl_detect) ? (1u << k) : 0u;
+#pragma unroll
+            for (int k = 0; k < SEG; ++k) my_box[k * TF] = box[k];  // parked: the write-out below indexes them dynamically
+            parked = true;
+          }
           pos = atomicAdd(a.slot_count + t, __popc(hits));
         }
       }
@@ -789,11 +807,19 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           if (over & ~covered) a.cand_flag[t] = 1;
         }
       }
-      if (hits) {  // detection entries of my (frame, segment), bins ascending; the per-frame list is ordered later (k_entries_sort)
-        DetectEntry* dst = a.slots + static_cast<size_t>(t) * a.slot_capacity;
+      if (hits == (1u << SEG) - 1u && pos + SEG <= a.slot_capacity) {  // the whole segment, straight from the registers
+        DetectEntry* dst = a.slots + slot_index(t, pos, a.slot_capacity);
+#pragma unroll
+        for (int k = 0; k < SEG; ++k) dst[k * 32] = DetectEntry{bin0 + k, value_of(box[k])};
+      } else if (hits) {  // detection entries of my (frame, segment), bins ascending; the per-frame list is ordered later (k_entries_sort)
+        if (!parked) {
+#pragma unroll
+          for (int k = 0; k < SEG; ++k) my_box[k * TF] = box[k];
+        }
+        DetectEntry* dst = a.slots + slot_index(t, 0, a.slot_capacity);
         for (unsigned int mm = hits; mm; mm &= mm - 1) {
           const int k = __ffs(mm) - 1;
-          if (pos < a.slot_capacity) dst[pos] = DetectEntry{bin0 + k, value_of(my_box[k * TF])};
+          if (pos < a.slot_capacity) dst[static_cast<size_t>(pos) * 32] = DetectEntry{bin0 + k, value_of(my_box[k * TF])};
           ++pos;
         }
       }
@@ -804,7 +830,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         btr_c[2] += b3c - b2c;
       }
     }
-    if (btr) printf("[k_detect cta %d] box warp g0 s0: wait FULL %lld, load+div+boxcar %lld, entries+rest %lld\n", blockIdx.x, btr_c[0], btr_c[1], btr_c[2]);
+    if (btr) printf("[k_detect cta %d] box warp g0 s%d: wait FULL %lld, load+div+boxcar %lld, entries+rest %lld\n", blockIdx.x, seg, btr_c[0], btr_c[1], btr_c[2]);
     if (a.cta_ns && btid == 0 && group == (n_tiles - 1) % kBoxGroups) a.cta_ns[2 * blockIdx.x + 1] = global_timer_ns();
   }
 }
@@ -865,12 +891,12 @@ __global__ void __launch_bounds__(256) k_entries_sort(const DetectEntry* slots, 
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_frames) return;
   const int count = min(slot_count[warp], capacity);
-  const DetectEntry* src = slots + static_cast<size_t>(warp) * capacity;
+  const DetectEntry* src = slots + slot_index(warp, 0, capacity);  // entry i of this frame: src[32 * i]
   DetectEntry* dst = out + offsets[warp];
   for (int i = lane; i < count; i += 32) {
-    const DetectEntry e = src[i];
+    const DetectEntry e = src[static_cast<size_t>(i) * 32];
     int rank = 0;
-    for (int k = 0; k < count; ++k) rank += (src[k].bin < e.bin) ? 1 : 0;
+    for (int k = 0; k < count; ++k) rank += (src[static_cast<size_t>(k) * 32].bin < e.bin) ? 1 : 0;
     dst[rank] = e;
   }
   if (!fold.count) return;

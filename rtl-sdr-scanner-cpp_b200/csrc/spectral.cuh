@@ -20,26 +20,31 @@ namespace b2s {
 // ------------------------------------------------------------------------------------------------------------
 // small DFTs in registers (forward transform, exp(-2 pi i k n / R)), natural-order in-place
 // ------------------------------------------------------------------------------------------------------------
+// C is the complex value type: float2 (scalar fp32 instructions) or cpk (packed two-wide instructions, b2s_device.cuh); the
+// operations are the same IEEE operations either way.
 template <int R>
 struct Dft;
 
 template <>
 struct Dft<1> {
-  __device__ __forceinline__ static void run(float2*) {}
+  template <typename C>
+  __device__ __forceinline__ static void run(C*) {}
 };
 template <>
 struct Dft<2> {
-  __device__ __forceinline__ static void run(float2* v) {
-    const float2 a = v[0], b = v[1];
+  template <typename C>
+  __device__ __forceinline__ static void run(C* v) {
+    const C a = v[0], b = v[1];
     v[0] = cadd(a, b);
     v[1] = csub(a, b);
   }
 };
 template <>
 struct Dft<4> {
-  __device__ __forceinline__ static void run(float2* v) {
-    const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
-    const float2 t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
+  template <typename C>
+  __device__ __forceinline__ static void run(C* v) {
+    const C t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    const C t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
     v[0] = cadd(t0, t2);
     v[1] = cadd(t1, t3);
     v[2] = csub(t0, t2);
@@ -48,19 +53,19 @@ struct Dft<4> {
 };
 
 // multiply by W_R^j = exp(-2 pi i j / R), j a compile-time constant after unrolling (R in {8, 16})
-template <int R>
-__device__ __forceinline__ float2 mul_w(float2 a, int j) {
+template <int R, typename C>
+__device__ __forceinline__ C mul_w(C a, int j) {
   constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
   const int j16 = j * (16 / R);  // express as a 16th root
   switch (j16 & 15) {
     case 0: return a;
     case 4: return mul_mi(a);
-    case 8: return make_float2(-a.x, -a.y);
-    case 12: return make_float2(-a.y, a.x);
-    case 2: return make_float2((a.x + a.y) * H, (a.y - a.x) * H);
-    case 6: return make_float2((a.y - a.x) * H, -(a.x + a.y) * H);
-    case 10: return make_float2(-(a.x + a.y) * H, (a.x - a.y) * H);
-    case 14: return make_float2((a.x - a.y) * H, (a.x + a.y) * H);
+    case 8: return cneg(a);
+    case 12: return cneg(mul_mi(a));
+    case 2: return cscale(cadd(a, mul_mi(a)), H);         // ((a.x + a.y) H, (a.y - a.x) H)
+    case 6: return cscale(csub(mul_mi(a), a), H);         // ((a.y - a.x) H, -(a.x + a.y) H)
+    case 10: return cscale(cneg(cadd(a, mul_mi(a))), H);  // (-(a.x + a.y) H, (a.x - a.y) H)
+    case 14: return cscale(csub(a, mul_mi(a)), H);        // ((a.x - a.y) H, (a.x + a.y) H)
     case 1: return cmul(a, make_float2(C1, -S1));
     case 3: return cmul(a, make_float2(S1, -C1));
     case 5: return cmul(a, make_float2(-S1, -C1));
@@ -75,12 +80,13 @@ __device__ __forceinline__ float2 mul_w(float2 a, int j) {
 // Cooley-Tukey R = 4 * (R/4): n = N2*n1 + n2, k = k1 + 4*k2
 template <int R>
 struct Dft {
-  __device__ __forceinline__ static void run(float2* v) {
+  template <typename C>
+  __device__ __forceinline__ static void run(C* v) {
     constexpr int N2 = R / 4;
-    float2 y[N2][4];
+    C y[N2][4];
 #pragma unroll
     for (int n2 = 0; n2 < N2; ++n2) {
-      float2 a[4];
+      C a[4];
 #pragma unroll
       for (int n1 = 0; n1 < 4; ++n1) a[n1] = v[N2 * n1 + n2];
       Dft<4>::run(a);
@@ -89,7 +95,7 @@ struct Dft {
     }
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
-      float2 b[N2];
+      C b[N2];
 #pragma unroll
       for (int n2 = 0; n2 < N2; ++n2) b[n2] = y[n2][k1];
       Dft<N2>::run(b);

@@ -24,7 +24,8 @@
 namespace b2s {
 
 // multiply by W32^j = exp(-2 pi i j / 32), j a compile-time constant after unrolling
-__device__ __forceinline__ float2 mul_w32(float2 a, int j) {
+template <typename C>
+__device__ __forceinline__ C mul_w32(C a, int j) {
   constexpr float C1 = 0.98078528040323043f, S1 = 0.19509032201612825f;  // pi/16
   constexpr float C2 = 0.92387953251128674f, S2 = 0.38268343236508977f;  // 2pi/16
   constexpr float C3 = 0.83146961230254524f, S3 = 0.55557023301960218f;  // 3pi/16
@@ -32,8 +33,8 @@ __device__ __forceinline__ float2 mul_w32(float2 a, int j) {
   switch (j & 31) {
     case 0: return a;
     case 8: return mul_mi(a);
-    case 16: return make_float2(-a.x, -a.y);
-    case 24: return make_float2(-a.y, a.x);
+    case 16: return cneg(a);
+    case 24: return cneg(mul_mi(a));
     case 1: return cmul(a, make_float2(C1, -S1));
     case 2: return cmul(a, make_float2(C2, -S2));
     case 3: return cmul(a, make_float2(C3, -S3));
@@ -58,11 +59,12 @@ __device__ __forceinline__ float2 mul_w32(float2 a, int j) {
 }
 
 // 32-point DFT in registers: Cooley-Tukey 4 x 8 (n = 8*n1 + n2, k = k1 + 4*k2)
-__device__ __forceinline__ void dft32(float2* v) {
-  float2 y[8][4];
+template <typename C>
+__device__ __forceinline__ void dft32(C* v) {
+  C y[8][4];
 #pragma unroll
   for (int n2 = 0; n2 < 8; ++n2) {
-    float2 a[4];
+    C a[4];
 #pragma unroll
     for (int n1 = 0; n1 < 4; ++n1) a[n1] = v[8 * n1 + n2];
     Dft<4>::run(a);
@@ -71,7 +73,7 @@ __device__ __forceinline__ void dft32(float2* v) {
   }
 #pragma unroll
   for (int k1 = 0; k1 < 4; ++k1) {
-    float2 b[8];
+    C b[8];
 #pragma unroll
     for (int n2 = 0; n2 < 8; ++n2) b[n2] = y[n2][k1];
     Dft<8>::run(b);
@@ -79,6 +81,34 @@ __device__ __forceinline__ void dft32(float2* v) {
     for (int k2 = 0; k2 < 8; ++k2) v[k1 + 4 * k2] = b[k2];
   }
 }
+
+// Complex value type of k_spectrum3: cpk = packed two-wide fp32 instructions (FADD2 / FMUL2 / FFMA2: a complex add is one
+// instruction, a complex multiplication two), float2 = scalar instructions (A/B builds: -DB2S_K1_PACKED=0). Passes B and C
+// are bound by instruction issue (profiles/r02_k_spectrum3_ncu_summary.txt), and two thirds of their instructions are fp32
+// arithmetic on complex pairs.
+#ifndef B2S_K1_PACKED
+#define B2S_K1_PACKED 1
+#endif
+// Measured A/B switches (all three on by default; DESIGN.md section 3 has the numbers):
+//   B2S_K1_PAIR_A      (RA < 16 only) pass A handles two ADJACENT columns per thread step: 4-byte sample loads, 8-byte window
+//                      loads, 16-byte twiddle loads and 16-byte exchange stores instead of twice as many half-width ones
+//   B2S_K1_DEFER_OUT   the dB row is gathered into registers, the block barrier follows at once, and the global stores (+ the
+//                      first-maximum search) are issued behind it, beside the next frame's pass A
+//   B2S_K1_LOAD_ORDER  passes B and C load their 32 inputs in the order the first radix-4 butterflies consume them
+#ifndef B2S_K1_PAIR_A
+#define B2S_K1_PAIR_A 1
+#endif
+#ifndef B2S_K1_DEFER_OUT
+#define B2S_K1_DEFER_OUT 1
+#endif
+#ifndef B2S_K1_LOAD_ORDER
+#define B2S_K1_LOAD_ORDER 1
+#endif
+#if B2S_K1_PACKED
+using K1Complex = cpk;
+#else
+using K1Complex = float2;
+#endif
 
 constexpr int kBlockPitch = 32 * 33;  // float2 elements per warp-owned block (32 rows of pitch 33 after pass B)
 
@@ -116,8 +146,9 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
   static_assert(!SPLIT || RA == 16, "the split mode runs 16384-point sub-transforms");
   static_assert(SPLIT_S == 1 || SPLIT_S == 2 || SPLIT_S == 4 || SPLIT_S == 8 || SPLIT_S == 16, "S");
   extern __shared__ __align__(128) unsigned char smem[];
-  float2* X = reinterpret_cast<float2*>(smem);                                 // [RA][kBlockPitch]
-  float2* twB = X + RA * kBlockPitch;                                          // [31][32]
+  using C = K1Complex;
+  C* X = reinterpret_cast<C*>(smem);                                           // [RA][kBlockPitch]
+  float2* twB = reinterpret_cast<float2*>(X + RA * kBlockPitch);               // [31][32]
   unsigned char* raw = reinterpret_cast<unsigned char*>(twB + 31 * 32);        // TMA mode: 2M bytes, or 2 x kSplitStageBytes (split)
   float* Xf = reinterpret_cast<float*>(X);
   __shared__ __align__(8) uint64_t full_bar[2];
@@ -161,6 +192,10 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     if (SPLIT) issue(item, 1, 1);
   }
 
+  constexpr bool kDefer = B2S_K1_DEFER_OUT && !SPLIT;
+  constexpr bool kPairA = B2S_K1_PAIR_A && RA < 16;  // measured: -2 % at N = 4096, -1 % at 8192, +1 % at 16384 and in the split mode
+  int pend_frame = -1;   // kDefer: frame whose first maximum is still being collected in red_i[(round - 1) & 1]
+  float pend_max = 0.0f;
   uint32_t parity = 0;   // non-split: phase of full_bar[0]
   uint32_t chunk_no = 0; // split: chunks consumed so far by this CTA (stage = chunk_no & 1, phase = (chunk_no >> 1) & 1)
   int round = 0;
@@ -180,32 +215,28 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
         for (int u = 0; u < pc / T; ++u) {  // independent points: their loads overlap
           const int i = tid + u * T;
           const int np = q * pc + i;
-          float2 acc = make_float2(0.0f, 0.0f);
+          C acc = cmake(C{}, 0.0f, 0.0f);
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             const int n = np + s * M;
             const float w = __ldg(&a.wscale[n]);
-            float2 xs;
+            C xs;
             if (MODE == kModeCs8Tma) {
               const char2 smp = reinterpret_cast<const char2*>(st + s * pc * 2)[i];
-              xs = make_float2(static_cast<float>(smp.x) * w, static_cast<float>(smp.y) * w);
+              xs = cscale(cmake(C{}, static_cast<float>(smp.x), static_cast<float>(smp.y)), w);
             } else if (MODE == kModeCs8Direct) {
               const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-              xs = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+              xs = cscale(cmake(C{}, static_cast<float>(fp[2 * n]), static_cast<float>(fp[2 * n + 1])), w);
             } else {
               const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-              xs = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+              xs = cscale(cmake(C{}, fp[2 * n], fp[2 * n + 1]), w);
             }
             if (s == 0) {  // W_S^0 = 1
               acc = xs;
             } else if (S == 2) {  // W_2^c = +-1
-              const float sign = c ? -1.0f : 1.0f;
-              acc.x = fmaf(sign, xs.x, acc.x);
-              acc.y = fmaf(sign, xs.y, acc.y);
+              acc = c ? csub(acc, xs) : cadd(acc, xs);
             } else {
-              const float2 ws = s_ws[s];
-              acc.x = fmaf(xs.x, ws.x, fmaf(-xs.y, ws.y, acc.x));
-              acc.y = fmaf(xs.x, ws.y, fmaf(xs.y, ws.x, acc.y));
+              acc = cmadd(xs, s_ws[s], acc);
             }
           }
           if (c != 0) acc = cmul(acc, __ldg(&twc[np]));
@@ -223,10 +254,52 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     // ---------------- pass A: radix RA over n0 (stride 1024), input = windowed int8 samples (or y_c) ----------------
     if (!SPLIT && MODE == kModeCs8Tma) mbar_wait(&full_bar[0], parity);
     parity ^= 1;
+    static_assert(BPT % 2 == 0, "pass A pairs adjacent columns");
+    if constexpr (kPairA) {
+#pragma unroll
+    for (int u = 0; u < BPT / 2; ++u) {
+      const int b = 2 * (tid + u * T);  // even: this step does columns b and b + 1
+      C v0[RA], v1[RA];
+#pragma unroll
+      for (int m = 0; m < RA; ++m) {
+        const int n = m * 1024 + b;
+        if (SPLIT) {  // in place: this thread alone reads and writes columns b, b + 1 of every block
+          const float4 x = *reinterpret_cast<const float4*>(&X[m * kBlockPitch + b]);
+          v0[m] = cmake(C{}, x.x, x.y);
+          v1[m] = cmake(C{}, x.z, x.w);
+        } else {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(a.wscale + n));
+          if (MODE == kModeCs8Tma) {
+            const char4 s = reinterpret_cast<const char4*>(raw)[n >> 1];
+            v0[m] = cscale(cmake(C{}, static_cast<float>(s.x), static_cast<float>(s.y)), w.x);
+            v1[m] = cscale(cmake(C{}, static_cast<float>(s.z), static_cast<float>(s.w)), w.y);
+          } else if (MODE == kModeCs8Direct) {
+            const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes) + 2 * n;
+            v0[m] = cscale(cmake(C{}, static_cast<float>(fp[0]), static_cast<float>(fp[1])), w.x);
+            v1[m] = cscale(cmake(C{}, static_cast<float>(fp[2]), static_cast<float>(fp[3])), w.y);
+          } else {
+            const float2* fp = reinterpret_cast<const float2*>(base + static_cast<long long>(frame) * a.frame_stride_bytes) + n;
+            const float2 x0 = fp[0], x1 = fp[1];
+            v0[m] = cscale(cmake(C{}, x0.x, x0.y), w.x);
+            v1[m] = cscale(cmake(C{}, x1.x, x1.y), w.y);
+          }
+        }
+      }
+      Dft<RA>::run(v0);
+      Dft<RA>::run(v1);
+      *reinterpret_cast<float4*>(&X[b]) = make_float4(cre(v0[0]), cim(v0[0]), cre(v1[0]), cim(v1[0]));
+#pragma unroll
+      for (int k0 = 1; k0 < RA; ++k0) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(twA + (k0 - 1) * 1024 + b));
+        const C r0 = cmul(v0[k0], make_float2(t.x, t.y)), r1 = cmul(v1[k0], make_float2(t.z, t.w));
+        *reinterpret_cast<float4*>(&X[k0 * kBlockPitch + b]) = make_float4(cre(r0), cim(r0), cre(r1), cim(r1));
+      }
+    }
+    } else {
 #pragma unroll
     for (int u = 0; u < BPT; ++u) {
       const int b = tid + u * T;  // 0..1023
-      float2 v[RA];
+      C v[RA];
 #pragma unroll
       for (int m = 0; m < RA; ++m) {
         const int n = m * 1024 + b;
@@ -236,13 +309,13 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
           const float w = __ldg(&a.wscale[n]);
           if (MODE == kModeCs8Tma) {
             const char2 s = reinterpret_cast<const char2*>(raw)[n];
-            v[m] = make_float2(static_cast<float>(s.x) * w, static_cast<float>(s.y) * w);
+            v[m] = cscale(cmake(C{}, static_cast<float>(s.x), static_cast<float>(s.y)), w);
           } else if (MODE == kModeCs8Direct) {
             const signed char* fp = reinterpret_cast<const signed char*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-            v[m] = make_float2(static_cast<float>(fp[2 * n]) * w, static_cast<float>(fp[2 * n + 1]) * w);
+            v[m] = cscale(cmake(C{}, static_cast<float>(fp[2 * n]), static_cast<float>(fp[2 * n + 1])), w);
           } else {
             const float* fp = reinterpret_cast<const float*>(base + static_cast<long long>(frame) * a.frame_stride_bytes);
-            v[m] = make_float2(fp[2 * n] * w, fp[2 * n + 1] * w);
+            v[m] = cscale(cmake(C{}, fp[2 * n], fp[2 * n + 1]), w);
           }
         }
       }
@@ -251,22 +324,43 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
 #pragma unroll
       for (int k0 = 1; k0 < RA; ++k0) X[k0 * kBlockPitch + b] = cmul(v[k0], __ldg(&twA[(k0 - 1) * 1024 + b]));
     }
+    }
     __syncthreads();
+    if (kDefer && tid == 0 && pend_frame >= 0) {  // the previous frame's first maximum: every thread's atomicMin precedes this barrier
+      a.peak_index[pend_frame] = red_i[(round + 1) & 1];
+      a.peak_value[pend_frame] = pend_max;
+    }
     const int next_item = s_item[(round + 1) & 1];
     if (!SPLIT && MODE == kModeCs8Tma && tid == 0 && next_item < n_items) issue(next_item, 0, 0);  // staging buffer consumed: fetch the next frame behind the remaining passes
     // ---------------- passes B and C: warp `warp` owns block k0 = warp ----------------
-    float2 v[32];
-    float2* blk = X + warp * kBlockPitch;
+    C v[32];
+    C* blk = X + warp * kBlockPitch;
+#if B2S_K1_LOAD_ORDER
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {  // in the order dft32's radix-4 butterflies take them: (n2 = 0: 0 8 16 24), (n2 = 1: 1 9 17 25), ...
+      const int m = 8 * (q & 3) + (q >> 2);
+      v[m] = blk[m * 32 + lane];
+    }
+#else
 #pragma unroll
     for (int m = 0; m < 32; ++m) v[m] = blk[m * 32 + lane];  // element (n1 = m, n2 = lane)
+#endif
     __syncwarp();                                             // every lane has its inputs before anyone overwrites the block
     dft32(v);
     blk[lane * 33] = v[0];
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) blk[lane * 33 + k1] = cmul(v[k1], twB[(k1 - 1) * 32 + lane]);  // transposed: [n2][k1], pitch 33
     __syncwarp();
+#if B2S_K1_LOAD_ORDER
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int m = 8 * (q & 3) + (q >> 2);
+      v[m] = blk[m * 33 + lane];
+    }
+#else
 #pragma unroll
     for (int m = 0; m < 32; ++m) v[m] = blk[m * 33 + lane];  // element (k1 = lane, n2 = m)
+#endif
     __syncwarp();
     dft32(v);
     // lane k1 holds X[k0 + RA*k1 + 32*RA*k2] in v[k2]: |X|^2/fs -> dB (psd.cpp:18), parked in the warp's block as [k2][k1]
@@ -275,16 +369,17 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     constexpr float kDbPerLog2 = 3.0102999566398120f;
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) {
-      const float pw = fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y) * a.inv_fs;
+      const float re = cre(v[k2]), im = cim(v[k2]);
+      const float pw = fmaf(re, re, im * im) * a.inv_fs;
       const float db = kDbPerLog2 * fast_log2(pw);
       res[k2 * 32 + lane] = DEBUG_LIN ? pw : db;
-      if (DEBUG_LIN) v[k2].x = db;
       best_v = fmaxf(best_v, db);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best_v = fmaxf(best_v, __shfl_xor_sync(0xffffffffu, best_v, o));
     if (lane == 0) red_v[warp] = best_v;
-    if (tid == 0) red_i[0] = 0x7fffffff;
+    const int ri = kDefer ? (round & 1) : 0;
+    if (tid == 0) red_i[ri] = 0x7fffffff;
     __syncthreads();
     // ---------------- output: 4 consecutive (local) bins per thread, stored at (bin + N/2) mod N ----------------
     float row_max = red_v[0];
@@ -310,17 +405,36 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
         if (o == row_max) best_i = min(best_i, j);
       }
     } else {
+      float4 og[M / (4 * T)];
+      if (kDefer) {  // gather the row into registers, release the exchange buffer, then store: the stores drain beside the next pass A
+#pragma unroll
+        for (int i = 0; i < M / (4 * T); ++i) {
+          const int bin = 4 * (tid + i * T);
+          const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
+          const int k0 = bin & (RA - 1);
+          const float* src = Xf + k2 * 32 + k1;
+          og[i].x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
+          og[i].y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
+          og[i].z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
+          og[i].w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
+        }
+        __syncthreads();  // the exchange buffer is free again
+      }
 #pragma unroll
       for (int i = 0; i < M / (4 * T); ++i) {
         const int bin = 4 * (tid + i * T);
         const int q = bin / RA, k1 = q & 31, k2 = q >> 5;
         const int k0 = bin & (RA - 1);
         float4 o;
-        const float* src = Xf + k2 * 32 + k1;
-        o.x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
-        o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
-        o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
-        o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
+        if (kDefer) {
+          o = og[i];
+        } else {
+          const float* src = Xf + k2 * 32 + k1;
+          o.x = src[(k0 + 0) * (2 * kBlockPitch + 2)];
+          o.y = src[(k0 + 1) * (2 * kBlockPitch + 2)];
+          o.z = src[(k0 + 2) * (2 * kBlockPitch + 2)];
+          o.w = src[(k0 + 3) * (2 * kBlockPitch + 2)];
+        }
         const int j = (bin + M / 2) & (M - 1);
         if (DEBUG_LIN) {  // debug instantiation: the block holds |X|^2/fs; dB is recomputed here
           *reinterpret_cast<float4*>(a.power_lin + static_cast<size_t>(frame) * N + j) = o;
@@ -336,9 +450,14 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
         if (o.w == row_max) best_i = min(best_i, j + 3);
       }
     }
-    if (best_i != 0x7fffffff) atomicMin(&red_i[0], best_i);
-    __syncthreads();  // the exchange buffer is free again; red_i is final
-    if (tid == 0) {
+    if (best_i != 0x7fffffff) atomicMin(&red_i[ri], best_i);
+    if (kDefer) {  // red_i[ri] is final after the next block barrier (pass A of the next item, or the one behind the loop)
+      pend_frame = frame;
+      pend_max = row_max;
+    } else {
+      __syncthreads();  // the exchange buffer is free again; red_i is final
+    }
+    if (!kDefer && tid == 0) {
       if (SPLIT) {  // first maximum over the S classes: larger value wins, equal values -> lower index
         atomicMax(a.peak_packed + frame, (static_cast<unsigned long long>(ordered_bits(row_max)) << 32) | (0xffffffffu - static_cast<unsigned int>(red_i[0])));
       } else {
@@ -348,6 +467,13 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     }
     item = next_item;
     ++round;
+  }
+  if (kDefer) {
+    __syncthreads();
+    if (tid == 0 && pend_frame >= 0) {
+      a.peak_index[pend_frame] = red_i[(round + 1) & 1];
+      a.peak_value[pend_frame] = pend_max;
+    }
   }
   // leave the counters zeroed for the next launch: the last CTA to get here resets them (every CTA has drawn its last item)
   if (tid == 0) {
