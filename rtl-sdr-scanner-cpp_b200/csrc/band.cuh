@@ -786,10 +786,16 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     if (const char* e = getenv("B2S_K2_BUFFERS")) da.n_buffers = std::max(2, std::min(da.n_buffers, atoi(e)));  // experiments
     const size_t smem = fixed + per_tile * da.n_buffers;
     const int grid = (n + detect_bins - 1) / detect_bins;
+    if ((rc = prepare_kernel(engine, k_detect<21, 10, 136>, kDetectThreads, 220 * 1024, nullptr))) return rc;
+    if ((rc = prepare_kernel(engine, k_detect<21, 10, 56>, kDetectThreads, 220 * 1024, nullptr))) return rc;
     if ((rc = prepare_kernel(engine, k_detect<21, 10>, kDetectThreads, 220 * 1024, nullptr))) return rc;
     if ((rc = prepare_kernel(engine, k_detect<0, -1>, kDetectThreads, 220 * 1024, nullptr))) return rc;
     if (profiling) CU(cudaEventRecord(s.ev[2], stream));
-    if (half == 10 && Y == 21) {
+    if (half == 10 && Y == 21 && width == 136 && !getenv("B2S_K2_RUNTIME_WIDTH")) {
+      k_detect<21, 10, 136><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);  // N >= 8192: 112 bins + 2 x 12 halo columns
+    } else if (half == 10 && Y == 21 && width == 56 && !getenv("B2S_K2_RUNTIME_WIDTH")) {
+      k_detect<21, 10, 56><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);   // N = 4096: 32 bins + 2 x 12
+    } else if (half == 10 && Y == 21) {
       k_detect<21, 10><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);
     } else {
       k_detect<0, -1><<<grid, kDetectThreads, smem, stream>>>(da, s.psd_map);

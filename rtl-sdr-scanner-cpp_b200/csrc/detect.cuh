@@ -330,15 +330,21 @@ __device__ __forceinline__ float spec_tile(const float* __restrict__ raw, int wi
 // Steady-state tiles (no learning frame, ring look-back inside the push, full tile, no dense debug rows) take a
 // register-resident fully unrolled march; all others a generic one with the same float operations in the same order
 // (bit-identical, tested).
-template <int Y_T, int HALF_T>
+// WIDTH_T: the CTA's column count (bins_per_cta + both halos) as a compile-time constant (136 = 112 bins + 2 x 12, the N = 16384 launch),
+// or 0 for the runtime value: with a constant the SUM warps' 32 tile loads per column take immediate offsets instead of 32 address
+// instructions on the kernel's critical warps.
+#ifndef B2S_K2_SPEC_INTERLEAVE
+#define B2S_K2_SPEC_INTERLEAVE 1  // the inline spectrogram chain is accumulated branch-free, so ptxas can fill the Averager chain's latency gaps with it
+#endif
+template <int Y_T, int HALF_T, int WIDTH_T = 0>
 __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __grid_constant__ CUtensorMap psd_map) {
   extern __shared__ __align__(128) float sm[];
   constexpr int TF = kDetectTileFrames;
   static_assert(Y_T <= TF, "the register-resident ring look-back needs Y <= tile frames");
   const int half = HALF_T >= 0 ? HALF_T : a.group_x / 2;
   const int hp = (half + 3) & ~3;                   // halo padded to a 16-byte multiple
-  const int bins = a.bins_per_cta;                  // bins owned by this CTA
-  const int width = bins + 2 * hp;                  // columns held by this CTA (<= kSumThreads)
+  const int bins = WIDTH_T > 0 ? WIDTH_T - 2 * hp : a.bins_per_cta;  // bins owned by this CTA
+  const int width = WIDTH_T > 0 ? WIDTH_T : bins + 2 * hp;          // columns held by this CTA (<= kSumThreads)
   const int tile_elems = TF * width;
   float* psd_tiles = sm;                            // [kDetectBuffers][TF][width] raw PSD rows (bulk-copy target)
   // averaged values (m_average) handed to the box warps, TRANSPOSED: [kAvgBuffers][width][kSumPitch] (column-major, pitch 33). The
@@ -449,13 +455,21 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           // ~40 frame values instead of 53 (no spills on the serial chain)
           constexpr int kSplit = TF / 2, kLate = kSplit - 4;
           const bool spec_here = spec_inline && spec_owner;
+#if B2S_K2_SPEC_INTERLEAVE
+          float sp = spec;  // accumulated by every thread, kept by the owners of an inline tile: no branch around the second chain
+#endif
           auto load_half = [&](int f0) {
 #pragma unroll
             for (int f = f0; f < f0 + kSplit; ++f) q[f] = cur[f * width];
+#if B2S_K2_SPEC_INTERLEAVE
+#pragma unroll
+            for (int f = f0; f < f0 + kSplit; ++f) sp = __fadd_rn(sp, q[f]);
+#else
             if (spec_here) {
 #pragma unroll
               for (int f = f0; f < f0 + kSplit; ++f) spec = __fadd_rn(spec, q[f]);
             }
+#endif
 #pragma unroll
             for (int f = f0; f < f0 + kSplit; ++f) q[f] = __fsub_rn(q[f], thr);  // NoiseLearner::work, noise_learner.cpp:54
           };
@@ -473,6 +487,9 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           asm volatile("" ::: "memory");  // keep the compiler from hoisting the second half's loads to the top
           load_half(kSplit);
           march(kLate, TF);
+#if B2S_K2_SPEC_INTERLEAVE
+          spec = spec_here ? sp : spec;
+#endif
         }
       } else if (active) {
         // ---- generic march (learning frames, first tile of a push, partial tiles, dense debug rows, runtime Y) ----
@@ -520,6 +537,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         tr_c[0] += c1 - c0;
         tr_c[1] += c2 - c1;
         tr_c[2] += c3 - c2;
+        tr_c[3] += clock64() - c3;
       }
       if (spec_owner && !spec_inline) {  // tiles with an emission, non-steady tiles
         const float* __restrict__ raw = cur;
@@ -547,7 +565,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
         for (int f = 0; f < YC; ++f) lead[f] = q[TF - YC + f];
       }
     }
-    if (tr) printf("[k_detect cta %d] SUM warp 0: total %lld cycles: wait tile %lld, wait EMPTY %lld, march %lld, rest %lld (%d tiles)\n", blockIdx.x, clock64() - tr_begin, tr_c[0], tr_c[1], tr_c[2], clock64() - tr_begin - tr_c[0] - tr_c[1] - tr_c[2], n_tiles);
+    if (tr) printf("[k_detect cta %d] SUM warp 0: total %lld cycles: wait tile %lld, wait EMPTY %lld, march %lld, arrive FULL %lld, rest %lld (%d tiles)\n", blockIdx.x, clock64() - tr_begin, tr_c[0], tr_c[1], tr_c[2], tr_c[3], clock64() - tr_begin - tr_c[0] - tr_c[1] - tr_c[2] - tr_c[3], n_tiles);
     if (spec_owner) a.spec_sum[j] = spec;
     if (owner) {
       a.threshold_out[j] = thr;
