@@ -276,6 +276,11 @@ static_assert(kDetectBinsPerCta / 2 <= kSpecThreads, "one SPEC thread per spectr
 #ifndef B2S_K2_DIAG
 #define B2S_K2_DIAG 0  // timing diagnostics only (wrong results): 1 = box warps skip the division and the boxcar, 2 = SUM warps skip the march
 #endif
+#ifndef B2S_K2_TRACE
+#define B2S_K2_TRACE 0  // 1: the per-role cycle trace (DetectArgs::trace_cta) is compiled in. It costs the traced roles ~16 registers of 64-bit
+                        // counters under the 80-register cap, so the shipped kernel leaves it out; build with -DB2S_K2_TRACE=1 to use it
+#endif
+constexpr bool kTrace = B2S_K2_TRACE != 0;
 #ifndef B2S_K2_EARLY_EMPTY
 #define B2S_K2_EARLY_EMPTY 1
 #endif
@@ -419,7 +424,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
 
     int ps = 0;            // PSD ring slot of the current tile and the parity of its mbarrier phase
     uint32_t ps_phase = 0;
-    const bool tr = a.trace_cta == static_cast<int>(blockIdx.x) && ct == 0;
+    const bool tr = kTrace && a.trace_cta == static_cast<int>(blockIdx.x) && ct == 0;
     long long tr_c[4] = {0, 0, 0, 0};
     const long long tr_begin = tr ? clock64() : 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
@@ -688,7 +693,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     const int b0 = seg * SEG, bin0 = j0 + b0;
     float* my_box = box_park + (group * kBoxWarps + seg) * SEG * TF + lane;  // [k * TF]: written and read by this lane only
     static_assert(kBoxGroups == 1 || kBoxGroups == 2, "group g takes the tiles with tile % kBoxGroups == g");
-    const bool btr = a.trace_cta == static_cast<int>(blockIdx.x) && group == 0 && btid == 32 * a.trace_seg;
+    const bool btr = kTrace && a.trace_cta == static_cast<int>(blockIdx.x) && group == 0 && btid == 32 * a.trace_seg;
     long long btr_c[3] = {0, 0, 0};
     for (int tile = group; tile < n_tiles; tile += kBoxGroups) {
       const int t0 = tile * TF;
