@@ -758,8 +758,6 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   for (int i = 0; i < n_emit; ++i) {
     da.emit_frame[i] = emit_frames[i];
     da.emit_div[i] = emit_divs[i];
-    const int tile = emit_frames[i] / kDetectTileFrames;
-    if (tile < 256) da.emit_tiles[tile >> 5] |= 1u << (tile & 31);
   }
   da.spec_rows = s.spec_rows.p;
   da.box_last = s.host_track ? nullptr : s.box_last.p;

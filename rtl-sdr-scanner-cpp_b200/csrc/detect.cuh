@@ -90,7 +90,6 @@ struct DetectArgs {
   int* cand_flag;            // [T] set to 1 when an uncovered candidate exists
   // rows to emit during this push, planned by the host from the frame clock (Spectrogram::send, spectrogram.cpp:62-75).
   // Carried in the kernel arguments so that no small host->device copy sits on the critical path behind the bulk IQ copy.
-  unsigned int emit_tiles[8];      // bit t: a row is emitted inside tile t of the push (max_frames <= 8192; beyond that every tile is checked)
   int n_emit;                      // <= kMaxSpecEmits
   int emit_frame[kMaxSpecEmits];   // frame after which row i is emitted (ascending)
   int emit_div[kMaxSpecEmits];     // Container::m_counter at that moment
@@ -421,6 +420,9 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     const bool spec_owner = owner && d == 1;  // decimating spectrograms (d > 1) are carried by the SPEC warps
     float spec = spec_owner ? a.spec_sum[j] : 0.0f;
     int next_emit = 0;  // index of the first planned spectrogram row not yet emitted (rows are in frame order)
+    // tile in which that row completes: ONE register compare per tile on the kernel's critical warps (the emission table lives in the
+    // kernel arguments; an indexed constant load + a scan per tile were 18 % of the SUM warps' stall samples)
+    int emit_tile = a.n_emit > 0 ? a.emit_frame[0] / TF : 0x7fffffff;
 
     int ps = 0;            // PSD ring slot of the current tile and the parity of its mbarrier phase
     uint32_t ps_phase = 0;
@@ -443,10 +445,7 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
       float checkpoint = 0.0f;
       // a spectrogram row completes inside this tile: one bit per tile, set by the host (a scan of the emission table with its
       // indexed constant loads sat on the serial chain's warps every tile)
-      const bool emits = tile < 256 ? ((a.emit_tiles[tile >> 5] >> (tile & 31)) & 1u) != 0u : a.n_emit > 0;
-      if (emits) {
-        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-      }
+      const bool emits = tile == emit_tile;
       const bool spec_inline = steady && d == 1 && !emits;
 #if B2S_K2_DIAG == 2
       if (steady) {
@@ -557,6 +556,10 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
           }
         }
       }
+      if (emits) {  // past this tile's rows
+        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + TF) ++next_emit;
+        emit_tile = next_emit < a.n_emit ? a.emit_frame[next_emit] / TF : 0x7fffffff;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[ps]);               // the PSD slot may be refilled
       if (++ps == a.n_buffers) {
@@ -641,18 +644,16 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
     float spec = on ? a.spec_sum[col] : 0.0f;
     const float inv_d = d > 0 ? 1.0f / static_cast<float>(d) : 0.0f;
     int next_emit = 0;
+    int emit_tile = a.n_emit > 0 ? a.emit_frame[0] / TF : 0x7fffffff;
     int ps = 0;
     uint32_t ps_phase = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int t0 = tile * TF;
       const int tf = min(TF, T - t0);
       mbar_wait_sleepy(&p_full[ps], ps_phase);
+      const bool emits = tile == emit_tile;
       if (on) {
         const float* __restrict__ raw = psd_tiles + ps * tile_elems + hp + sc * d;
-        const bool emits = tile < 256 ? ((a.emit_tiles[tile >> 5] >> (tile & 31)) & 1u) != 0u : a.n_emit > 0;
-        if (emits) {
-          while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0) ++next_emit;
-        }
         if (!emits && tf == TF && d <= 16) {
           switch (d) {
             case 2: spec = spec_tile<2>(raw, width, spec); break;
@@ -673,6 +674,10 @@ __global__ void __maxnreg__(kDetectRegs) k_detect(const DetectArgs a, const __gr
             }
           }
         }
+      }
+      if (emits) {
+        while (next_emit < a.n_emit && a.emit_frame[next_emit] < t0 + TF) ++next_emit;
+        emit_tile = next_emit < a.n_emit ? a.emit_frame[next_emit] / TF : 0x7fffffff;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_empty[ps]);
