@@ -92,6 +92,12 @@ typedef struct b2s_band_config {
   /* ---- engine-only sizing (ignored by the oracle) ---- */
   int32_t max_frames_per_push;  /* capacity of the per-push device buffers; 0 -> 4096 */
   int32_t detect_capacity;      /* detection entries kept per FRAME (bins >= min(start,stop)); 0 -> clamp(N/8, 256, 4096); grows on overflow */
+  /* ---- noise learning on the frame clock (read by the engine AND the oracle) ---- */
+  int64_t noise_learning_ms;    /* > 0: NoiseLearner's own rule (noise_learner.cpp:11,23): a centre frequency is learned from its first frame
+                                   (stamped s) up to and including the first frame stamped >= s + noise_learning_ms, however many frames
+                                   that is - under a hop schedule the time spent on other centres counts, as in the reference;
+                                   learn_frames is ignored. 0: learn_frames frames per centre (equal for a band that never hops).
+                                   b2s_default_config sets NOISE_LEARNING_TIME = 2000 (config.h:24). */
 } b2s_band_config;
 
 /* Fill cfg with the reference's defaults for a device with this sample rate, exactly as setupChains sizes the chain

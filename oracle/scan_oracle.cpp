@@ -309,18 +309,26 @@ struct RingAverager {
   }
 };
 
-// sources/radio/blocks/noise_learner.cpp:11-28 with the wall clock replaced by a frame count.
+// sources/radio/blocks/noise_learner.cpp:11-28 on the injected frame clock. learningMs > 0: the reference's own rule - m_startLearningTime
+// is the stamp of the first frame this centre sees (Noise() runs inside the first work() call, :9,42), and the frame whose stamp reaches
+// start + NOISE_LEARNING_TIME is the last learning frame (:23). learningMs == 0: a frame count instead of the clock.
 struct NoiseState {
   std::vector<float> threshold;
   int samples = 0;
   bool ready = false;
+  bool started = false;
+  int64_t start = 0;
   // returns true when this frame completes (or already completed) learning
-  bool add(const float* data, int size, int learnFrames) {
+  bool add(const float* data, int size, int learnFrames, int64_t now, int64_t learningMs) {
     if (ready) return true;
+    if (!started) {
+      started = true;
+      start = now;
+    }
     if (static_cast<int>(threshold.size()) < size) threshold.resize(size, -std::numeric_limits<float>::max());
     for (int i = 0; i < size; ++i) threshold[i] = std::max(threshold[i], data[i]);
     samples++;
-    if (learnFrames <= samples) {
+    if (learningMs > 0 ? start + learningMs <= now : learnFrames <= samples) {
       ready = true;
       return true;
     }
@@ -582,7 +590,7 @@ struct orc_chain {
       NoiseState& ns = noise[center];
       int peak = -1;
       if (!ns.ready) {
-        ns.add(psd.data(), n, cfg.learn_frames);
+        ns.add(psd.data(), n, cfg.learn_frames, now, cfg.noise_learning_ms);
         for (int j = 0; j < n; ++j) sub[j] = kNoData;  // also on the frame that completes learning (:45-51)
       } else {
         peak = 0;

@@ -59,6 +59,10 @@ typedef struct orc_config {
   int32_t spectrogram_out_size; /* min(16384, getFft(fs, 1000)), spectrogram.cpp:14 ; 0 = disabled */
   int64_t spectrogram_interval_ms; /* SPECTROGRAM_SEND_INTERVAL = 1000 */
   int32_t flags;                /* oracle: bit0 = use the fp32 FFT (timed CPU baseline) instead of fp64 */
+  int32_t engine_max_frames_per_push; /* (engine-only sizing fields of b2s_band_config: same layout, not read here) */
+  int32_t engine_detect_capacity;
+  int64_t noise_learning_ms;    /* > 0: Noise::add's wall-clock rule on the injected frame clock (noise_learner.cpp:11,23): ready after the first
+                                   frame stamped >= (stamp of the centre's first frame) + noise_learning_ms; 0: learn_frames frames */
 } orc_config;
 
 /* Optional dense per-frame outputs; any pointer may be NULL. */

@@ -55,6 +55,7 @@ class BandConfig(C.Structure):
         ("flags", C.c_int32),
         ("max_frames_per_push", C.c_int32),
         ("detect_capacity", C.c_int32),
+        ("noise_learning_ms", C.c_int64),
     ]
 
 
@@ -126,6 +127,7 @@ def make_config(
     max_frames_per_push: int = 0,
     detect_capacity: int = 0,
     flags: int = 0,
+    noise_learning_ms: int = 0,
 ) -> BandConfig:
     """Reference defaults (config.h:24-38, config.example.json:9-13, sdr_device.cpp:148-152) for an explicit N."""
     import math
@@ -162,6 +164,7 @@ def make_config(
     cfg.flags = flags
     cfg.max_frames_per_push = max_frames_per_push
     cfg.detect_capacity = detect_capacity
+    cfg.noise_learning_ms = noise_learning_ms  # 0: learn_frames frames per centre; > 0: the reference's wall-clock rule (noise_learner.cpp:23)
     return cfg
 
 

@@ -330,6 +330,7 @@ int validate_config(const b2s_band_config& c) {
   if (c.grouping_y < 1 || c.grouping_y > 256) return fail(B2S_E_INVALID, "grouping_y must be in 1..256");
   if (c.group_size_bins < 0 || c.group_size_bins > 4096) return fail(B2S_E_INVALID, "group_size_bins must be in 0..4096");
   if (c.learn_frames < 1) return fail(B2S_E_INVALID, "learn_frames must be >= 1");
+  if (c.noise_learning_ms < 0) return fail(B2S_E_INVALID, "noise_learning_ms must be >= 0 (0 = count learn_frames frames)");
   if (c.n_ignored < 0 || c.n_ignored > B2S_MAX_IGNORED) return fail(B2S_E_INVALID, "n_ignored out of range");
   if (c.tuning_step_hz <= 0) return fail(B2S_E_INVALID, "tuning_step_hz must be positive");
   if (c.spectrogram_out_size < 0 || (c.spectrogram_out_size > 0 && (!is_pow2(c.spectrogram_out_size) || c.spectrogram_out_size > c.fft_size ||
@@ -412,7 +413,7 @@ struct b2s_recorder {
   struct Stage {
     int interp = 1, decim = 1, n_taps = 0, hc = 0;
     std::vector<float> h_taps;
-    DevBuf<float> taps;
+    DevBuf<float> taps, taps_pq;  // taps_pq: [decim][kPolyQ] polyphase layout for k_decimate_poly (decimating stages), else empty
     DevBuf<float2> buf;      // stages >= 1: [hc carried samples | the previous stage's outputs of this push]
     long long consumed = 0;  // input samples seen since startRecording
     long long produced = 0;  // output samples produced since startRecording
@@ -424,6 +425,7 @@ struct b2s_recorder {
   ~b2s_recorder() {
     for (auto& st : stages) {
       st.taps.release();
+      st.taps_pq.release();
       st.buf.release();
     }
     carry_raw.release();
@@ -523,6 +525,7 @@ void b2s_default_config(b2s_band_config* cfg, int32_t sample_rate_hz, int32_t ce
   cfg->stop_level = 5.0f;
   const double period = static_cast<double>(cfg->frame_stride_samples) * 1000.0 / sample_rate_hz;
   cfg->learn_frames = b2s_learn_frames_from_ms(2000, period);
+  cfg->noise_learning_ms = 2000;  // NOISE_LEARNING_TIME (config.h:24): the reference's wall-clock rule on the frame clock
   cfg->center_hz = center_hz;
   cfg->range_lo_hz = center_hz - sample_rate_hz / 2;
   cfg->range_hi_hz = center_hz + sample_rate_hz / 2;
@@ -1029,6 +1032,12 @@ int b2s_recorder_create(b2s_engine* e, int32_t sample_rate_hz, int32_t bandwidth
     if (st.hc > 4096) rc = fail(B2S_E_INVALID, "resampler stage %d/%d needs %d samples of history", st.interp, st.decim, st.hc);
     if (!rc) rc = st.taps.alloc(st.n_taps);
     if (!rc && cudaMemcpy(st.taps.p, st.h_taps.data(), sizeof(float) * st.n_taps, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(B2S_E_CUDA, "taps upload failed");
+    if (!rc && st.interp == 1 && st.decim >= 2 && (st.n_taps + st.decim - 1) / st.decim <= kPolyQ && !getenv("B2S_RECORDER_GENERIC")) {
+      std::vector<float> pq(static_cast<size_t>(st.decim) * kPolyQ, 0.0f);  // h[q D + p] at [p][q], zero padded
+      for (int k = 0; k < st.n_taps; ++k) pq[static_cast<size_t>(k % st.decim) * kPolyQ + k / st.decim] = st.h_taps[k];
+      rc = st.taps_pq.alloc(pq.size());
+      if (!rc && cudaMemcpy(st.taps_pq.p, pq.data(), sizeof(float) * pq.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(B2S_E_CUDA, "taps upload failed");
+    }
     if (!rc && r->stages.size() > 1) rc = st.buf.alloc(st.hc + n_in + 2);
     n_in = (n_in * st.interp) / st.decim + 2;
   }
@@ -1123,7 +1132,10 @@ int b2s_recorder_push(b2s_recorder* r, const void* iq, size_t n_samples, int8_t*
     float2* next_buf = last ? nullptr : r->stages[si + 1].buf.p;
     a.out_f = last ? nullptr : next_buf + r->stages[si + 1].hc;
     a.out_i8 = last ? r->d_out.p : nullptr;
-    if (n_new > 0) {
+    if (n_new > 0 && st.taps_pq.p) {  // decimating stage: polyphase kernel
+      k_decimate_poly<<<static_cast<int>((n_new + kPolyOut - 1) / kPolyOut), kPolyThreads, 0, r->stream>>>(a, st.taps_pq.p);
+      CU(cudaGetLastError());
+    } else if (n_new > 0) {
       const int grid = static_cast<int>((n_new + a.per_cta - 1) / a.per_cta);
       k_resample<<<grid, kResampleThreads, sizeof(float2) * kResampleTile, r->stream>>>(a);
       CU(cudaGetLastError());

@@ -21,6 +21,10 @@ struct NoiseSlot {
   float* now() { return threshold[cur].p; }
   int samples = 0;
   bool ready = false;
+  // noise_learning_ms > 0 (NoiseLearner's own rule): Noise::m_startLearningTime = the stamp of the first frame this centre saw
+  // (noise_learner.cpp:9,42: Noise() runs inside the first work() call on that centre)
+  bool started = false;
+  int64_t start_ms = 0;
 };
 struct SpectroSlot {
   DevBuf<float> sum;
@@ -66,7 +70,7 @@ struct PushSlot {
   int64_t t0_ms = 0;
   double period_ms = 0.0;
   size_t frame_offset = 0;
-  int noise_samples = 0, avg_frames_before = 0, ring_before = 0;
+  int noise_samples = 0, learn_frames = 0, avg_frames_before = 0, ring_before = 0;  // frame t of the push was a learning frame iff noise_samples + t < learn_frames
   const float* threshold = nullptr;
   int32_t center = 0;
   int n_emit = 0;
@@ -217,7 +221,7 @@ struct b2s_band : public DeviceQueries {
       const int f = frame_first + r;
       if (f < 0) continue;
       float* dst = out + static_cast<size_t>(r) * width;
-      if (s.noise_samples + f < cfg.learn_frames) {
+      if (s.noise_samples + f < s.learn_frames) {
         for (int i = 0; i < width; ++i) dst[i] = kNoData;
       } else {
         for (int i = 0; i < width; ++i) dst[i] = dst[i] - s.thr_host[bin_lo + i];  // same IEEE subtraction as the kernel
@@ -259,7 +263,7 @@ struct b2s_band : public DeviceQueries {
     a.psd = s.psd.p;
     a.threshold = s.threshold;
     a.noise_samples = s.noise_samples;
-    a.learn_frames = cfg.learn_frames;
+    a.learn_frames = s.learn_frames;
     a.ring_in = d_ring[s.ring_before].p;
     a.avg_frames = s.avg_frames_before;
     a.checkpoints = s.ckpt.p;
@@ -731,8 +735,35 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   da.psd = s.psd.p;
   da.threshold = ns->threshold[ns->cur].p;
   da.threshold_out = ns->threshold[ns->cur ^ 1].p;
-  da.noise_samples = ns->ready ? cfg.learn_frames : ns->samples;
-  da.learn_frames = cfg.learn_frames;
+  // learning frames of this push: frame t is one iff noise_samples + t < learn_frames (K2, K3 and K4 share the predicate)
+  bool ready_after = ns->ready;
+  int learned_here = 0;
+  if (ns->ready) {
+    da.noise_samples = da.learn_frames = 0;
+  } else if (cfg.noise_learning_ms > 0) {
+    // NoiseLearner's own rule on the frame clock (noise_learner.cpp:11,23): every frame up to AND INCLUDING the first one stamped at or
+    // after start + NOISE_LEARNING_TIME is a learning frame; the time the band spent on other centres counts
+    if (!ns->started) {
+      ns->started = true;
+      ns->start_ms = host::frame_time(t0_ms, period_ms, frame_offset);
+    }
+    int last = -1;
+    for (int t = 0; t < T; ++t) {
+      if (ns->start_ms + cfg.noise_learning_ms <= host::frame_time(t0_ms, period_ms, frame_offset + t)) {
+        last = t;
+        break;
+      }
+    }
+    da.noise_samples = 0;
+    da.learn_frames = last >= 0 ? last + 1 : T + 1;  // T + 1: all T frames of this push, and not finished
+    learned_here = last >= 0 ? last + 1 : T;
+    ready_after = last >= 0;
+  } else {
+    da.noise_samples = ns->samples;
+    da.learn_frames = cfg.learn_frames;
+    learned_here = std::min(T, cfg.learn_frames - ns->samples);
+    ready_after = ns->samples + T >= cfg.learn_frames;
+  }
   da.avg_sum = d_sum[sum_cur].p;
   da.avg_sum_out = d_sum[sum_cur ^ 1].p;
   da.ring_in = d_ring[ring_in].p;
@@ -843,7 +874,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
     ta.psd = s.psd.p;
     ta.threshold = da.threshold_out;
     ta.noise_samples = da.noise_samples;
-    ta.learn_frames = cfg.learn_frames;
+    ta.learn_frames = da.learn_frames;
     ta.ring_before = d_ring[ring_in].p;
     ta.state = d_state.p;
     ta.result = s.d_result.p;
@@ -872,6 +903,7 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   s.period_ms = period_ms;
   s.frame_offset = frame_offset;
   s.noise_samples = da.noise_samples;
+  s.learn_frames = da.learn_frames;
   s.avg_frames_before = avg_frames;
   s.ring_before = ring_in;
   s.threshold = da.threshold_out;  // the thresholds as of the end of this push
@@ -881,8 +913,8 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   s.thr_host_valid = false;
   // host mirrors of the scalar state advance at enqueue time (they do not depend on the results)
   if (!ns->ready) {
-    ns->samples = std::min(ns->samples + T, cfg.learn_frames);
-    ns->ready = ns->samples >= cfg.learn_frames;
+    ns->samples += learned_here;
+    ns->ready = ready_after;
   }
   ns->cur ^= 1;
   sum_cur ^= 1;

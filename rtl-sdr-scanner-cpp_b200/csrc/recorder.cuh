@@ -41,22 +41,30 @@ struct ResampleArgs {
   signed char* out_i8;   // ... the int8 pairs of the last stage
 };
 
-__device__ __forceinline__ float2 resample_input(const ResampleArgs& a, long long g) {
-  if (g < 0) return make_float2(0.0f, 0.0f);  // before startRecording: zero history
+// sample g of this stage's input stream, before the rotator (zero before startRecording)
+__device__ __forceinline__ float2 resample_raw(const ResampleArgs& a, long long g) {
+  if (g < 0) return make_float2(0.0f, 0.0f);
   const long long rel = g - a.g0;
-  float2 v;
-  if (a.kind == 2) {
-    const float2* p = rel >= 0 ? static_cast<const float2*>(a.in) + rel : static_cast<const float2*>(a.carry) + (a.hc + rel);
-    return *p;
-  }
+  if (rel >= a.n_in) return make_float2(0.0f, 0.0f);  // past the newest sample (the last CTA of k_decimate_poly stages a whole tile; only unused outputs see these)
   if (a.kind == 0) {
     const char2* p = rel >= 0 ? static_cast<const char2*>(a.in) + rel : static_cast<const char2*>(a.carry) + (a.hc + rel);
     const char2 s = *p;
-    v = make_float2(static_cast<float>(s.x) * a.iq_scale, static_cast<float>(s.y) * a.iq_scale);
-  } else {
-    const float2* p = rel >= 0 ? static_cast<const float2*>(a.in) + rel : static_cast<const float2*>(a.carry) + (a.hc + rel);
-    v = *p;
+    return make_float2(static_cast<float>(s.x) * a.iq_scale, static_cast<float>(s.y) * a.iq_scale);
   }
+  const float2* p = rel >= 0 ? static_cast<const float2*>(a.in) + rel : static_cast<const float2*>(a.carry) + (a.hc + rel);
+  return *p;
+}
+// exp(i * 2 pi * turns), turns as a 64-bit binary fraction
+__device__ __forceinline__ float2 rotor_of(unsigned long long turns64) {
+  float sn, cs;
+  sincospif(static_cast<float>(static_cast<unsigned int>(turns64 >> 32)) * (2.0f / 4294967296.0f), &sn, &cs);
+  return make_float2(cs, sn);
+}
+
+__device__ __forceinline__ float2 resample_input(const ResampleArgs& a, long long g) {
+  if (g < 0) return make_float2(0.0f, 0.0f);  // before startRecording: zero history
+  float2 v = resample_raw(a, g);
+  if (a.kind == 2) return v;
   if (a.phase_inc) {  // rotator_cc: x[n] * exp(i * phase_inc * n)
     const unsigned long long ph = static_cast<unsigned long long>(g) * a.phase_inc;  // turns * 2^64, modulo 1 turn by overflow
     float sn, cs;
@@ -98,6 +106,82 @@ __global__ void __launch_bounds__(kResampleThreads) k_resample(const ResampleArg
       a.out_i8[2 * oi + 1] = static_cast<signed char>(q);
     } else {
       a.out_f[oi] = make_float2(re, im);
+    }
+  }
+}
+
+// Decimating stages (interpolation 1 — every stage the reference's factor pairs produce for a recorder below the device rate) in
+// polyphase form: k = q D + p,   y[m] = sum_p sum_q h[q D + p] x[(m - q) D - p].
+// A CTA produces kPolyOut consecutive outputs. It walks the D phases; for phase p it stages x_p[n] = x[(m0 - (Q - 1) + n) D - p]
+// (rotated on the way in: one sincospif per thread and phase, then a constant rotor per step — the 64-bit phase accumulator still
+// anchors every phase of every CTA, so there is no drift) into one of two shared tiles, and every thread accumulates kPolyR
+// consecutive outputs from a register window of kPolyR + Q - 1 samples of that phase: 33 x 9 complex multiply-adds per 41 shared
+// loads and 33 broadcast tap loads, against one shared load and one global tap load per multiply-add in k_resample. The lane stride
+// of the window (9 samples = 18 words) is conflict-free for 8-byte accesses.
+constexpr int kPolyQ = 33;        // taps per phase: GNU Radio's default design has ceil(n_taps / D) = 33 for every D
+constexpr int kPolyR = 9;         // outputs per thread
+constexpr int kPolyThreads = 128;
+constexpr int kPolyOut = kPolyThreads * kPolyR;   // outputs per CTA
+constexpr int kPolyTile = kPolyOut + kPolyQ - 1;  // samples of one phase a CTA needs
+
+__global__ void __launch_bounds__(kPolyThreads) k_decimate_poly(const ResampleArgs a, const float* __restrict__ taps_pq /* [D][kPolyQ]: h[q D + p], zero padded */) {
+  __shared__ float2 tile[2][kPolyTile];
+  __shared__ float htap[2][kPolyQ];
+  const int tid = threadIdx.x;
+  const int D = a.decim;
+  const long long mb = a.m0 + static_cast<long long>(blockIdx.x) * kPolyOut;  // first output of this CTA
+  const int count = min(kPolyOut, a.n_out - static_cast<int>(blockIdx.x) * kPolyOut);
+  if (count <= 0) return;
+  const bool rotate = a.kind != 2 && a.phase_inc != 0;
+  // rotor of kPolyThreads tile steps = kPolyThreads * D input samples
+  const float2 rstep = rotate ? rotor_of(static_cast<unsigned long long>(kPolyThreads) * static_cast<unsigned long long>(D) * a.phase_inc) : make_float2(1.0f, 0.0f);
+  auto fill = [&](int p, int buf) {
+    long long g = (mb - (kPolyQ - 1) + tid) * D - p;  // input sample under tile element n = tid
+    float2 r = rotate ? rotor_of(static_cast<unsigned long long>(g) * a.phase_inc) : make_float2(1.0f, 0.0f);
+    for (int n = tid; n < kPolyTile; n += kPolyThreads, g += static_cast<long long>(kPolyThreads) * D) {
+      float2 v = resample_raw(a, g);
+      if (rotate) {
+        v = make_float2(fmaf(v.x, r.x, -v.y * r.y), fmaf(v.x, r.y, v.y * r.x));
+        r = make_float2(fmaf(r.x, rstep.x, -r.y * rstep.y), fmaf(r.x, rstep.y, r.y * rstep.x));
+      }
+      tile[buf][n] = v;
+    }
+    if (tid < kPolyQ) htap[buf][tid] = taps_pq[p * kPolyQ + tid];
+  };
+  float2 acc[kPolyR];
+#pragma unroll
+  for (int r = 0; r < kPolyR; ++r) acc[r] = make_float2(0.0f, 0.0f);
+  fill(0, 0);
+  __syncthreads();
+  for (int p = 0; p < D; ++p) {
+    if (p + 1 < D) fill(p + 1, (p + 1) & 1);
+    const float2* w = tile[p & 1] + tid * kPolyR;  // w[j] = x_p[tid R + j]; output r, tap q reads j = r + (Q - 1) - q
+    float2 win[kPolyR + kPolyQ - 1];
+#pragma unroll
+    for (int j = 0; j < kPolyR + kPolyQ - 1; ++j) win[j] = w[j];
+    const float* h = htap[p & 1];
+#pragma unroll
+    for (int q = 0; q < kPolyQ; ++q) {
+      const float hq = h[q];
+#pragma unroll
+      for (int r = 0; r < kPolyR; ++r) {
+        acc[r].x = fmaf(hq, win[r + kPolyQ - 1 - q].x, acc[r].x);
+        acc[r].y = fmaf(hq, win[r + kPolyQ - 1 - q].y, acc[r].y);
+      }
+    }
+    __syncthreads();  // tile[(p + 1) & 1] is filled, tile[p & 1] is free
+  }
+#pragma unroll
+  for (int r = 0; r < kPolyR; ++r) {
+    const int o = tid * kPolyR + r;
+    if (o < count) {
+      const long long oi = mb + o - a.m0;
+      if (a.out_i8) {  // complex_to_interleaved_char(vector, 127): rint, saturate
+        const int re = max(-128, min(127, __float2int_rn(acc[r].x * 127.0f))), im = max(-128, min(127, __float2int_rn(acc[r].y * 127.0f)));
+        reinterpret_cast<char2*>(a.out_i8)[oi] = make_char2(static_cast<signed char>(re), static_cast<signed char>(im));
+      } else {
+        a.out_f[oi] = acc[r];
+      }
     }
   }
 }

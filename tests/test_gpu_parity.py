@@ -431,6 +431,39 @@ def test_reset_and_retune_semantics(engine):
     assert np.array_equal(band.get_noise()[0], thr0)
 
 
+def test_noise_learning_on_the_frame_clock_under_a_hop_schedule(engine):
+    """noise_learning_ms (NoiseLearner's own wall-clock rule, noise_learner.cpp:11,23) through the engine: two centres visited alternately for
+    500 ms each; the engine's learning frames, rows and per-frame lists equal the oracle's (which is pinned against the compiled reference
+    NoiseLearner under the same schedule, tests/test_oracle_vs_reference_blocks.py)."""
+    n, fs, dwell, hops = 1024, 2_048_000, 20, 14
+    period = 25.0
+    cfg = b2s.make_config(n, fs, learn_frames=10_000, noise_learning_ms=2000, recording_bandwidth_hz=16 * fs // n, min_time_ms=200, timeout_ms=300)
+    frames = dwell * hops
+    iq = synth.make_iq_int8(n, frames, synth.standard_scene(n, frames, 0), seed=synth.seed_for(11), quiet_frames=0)
+    band, o = b2s.Band(engine, cfg), ol.OracleChain(cfg)
+    centres = [cfg.center_hz, cfg.center_hz + 3_000_000]
+    real_rows = 0
+    for h in range(hops):
+        c = centres[h % 2]
+        band.reset(), o.reset()
+        band.set_center(c, c - fs // 2, c + fs // 2), o.set_center(c, c - fs // 2, c + fs // 2)
+        k0 = h * dwell
+        t0 = int(np.floor(k0 * period + 0.5))
+        part = iq[k0 * 2 * n : (k0 + dwell) * 2 * n]
+        g = band.push(part, dwell, t0, period, per_frame=True, dense=("noise_sub_db",))
+        r = o.push(part, dwell, t0, period, dense=("psd_db", "noise_sub_db"))
+        learning_g = np.all(g.noise_sub_db == -100.0, axis=1)
+        learning_r = np.all(r.noise_sub_db == -100.0, axis=1)
+        assert np.array_equal(learning_g, learning_r), f"hop {h}: learning frames {np.nonzero(learning_g)[0]} vs {np.nonzero(learning_r)[0]}"
+        if (~learning_r).any():
+            main = r.psd_db[~learning_r] >= np.median(r.psd_db[~learning_r], axis=1, keepdims=True) - 10.0
+            assert np.max(np.abs(g.noise_sub_db[~learning_r] - r.noise_sub_db[~learning_r])[main]) <= 4e-3
+            real_rows += int((~learning_r).sum())
+        assert _tx(g.frame_tx) == _tx(r.frame_tx), f"hop {h}"
+        assert band.get_noise()[1:] == o.get_noise()[1:]  # (samples, ready) of the current centre
+    assert real_rows == frames - 82  # 41 learning frames per centre, not 2 x 81 frames of dwell
+
+
 def test_ignored_ranges_and_scan_range(engine):
     n, fs, frames, learn = 1024, 2_048_000, 300, 40
     base, tones, iq, period = scene(n, fs, frames, learn)

@@ -101,6 +101,41 @@ def test_hop_and_reset_follow_the_reference_objects():
         assert tx == [(f, fl) for f, fl, _, _ in r2.frame_tx[k]], f"frame {k} after the hop"
 
 
+def test_noise_learning_follows_the_reference_clock_under_a_hop_schedule():
+    """Scanner hops every 500 ms (RANGE_SCANNING_TIME) between two centres: the reference's Noise finishes NOISE_LEARNING_TIME after the FIRST
+    visit of a centre (noise_learner.cpp:11,23), the time spent on the other centre included — not after 2 s of dwell. The oracle's clock rule
+    (noise_learning_ms) must give the same learning frames, rows and transmission lists as the compiled NoiseLearner / Transmission."""
+    n, fs, dwell, hops = 1024, 2_048_000, 20, 14  # 20 frames x 25 ms = 500 ms per visit
+    bw = 16 * fs // n
+    cfg = b2s.make_config(n, fs, learn_frames=10_000, noise_learning_ms=NOISE_LEARNING_MS, recording_bandwidth_hz=bw, min_time_ms=200, timeout_ms=300)
+    frames = dwell * hops
+    tones = synth.standard_scene(n, frames, 0)
+    iq = synth.make_iq_int8(n, frames, tones, seed=synth.seed_for(11), quiet_frames=0)
+    centres = [cfg.center_hz, cfg.center_hz + 3_000_000]
+    orc = ol.OracleChain(cfg)
+    ref = ol.RefBlocksChain(cfg, _now(0), bw, with_spectrogram=False)
+    learning_frames = {c: 0 for c in centres}
+    first_real = {}
+    for h in range(hops):
+        c = centres[h % 2]
+        orc.reset(), ref.reset()  # SdrDevice::setFrequencyRange: resetBuffers on every retune (sdr_device.cpp:74)
+        orc.set_center(c, c - fs // 2, c + fs // 2), ref.set_center(c, c - fs // 2, c + fs // 2)
+        k0 = h * dwell
+        r = orc.push(iq[k0 * 2 * n : (k0 + dwell) * 2 * n], dwell, _now(k0), PERIOD_MS, dense=("psd_db", "noise_sub_db"))
+        for k in range(dwell):
+            q, tx = ref.push_row(r.psd_db[k], _now(k0) + int(np.floor(k * PERIOD_MS + 0.5)))
+            assert np.array_equal(q.view(np.uint32), r.noise_sub_db[k].view(np.uint32)), f"hop {h} frame {k}"
+            assert tx == [(f, fl) for f, fl, _, _ in r.frame_tx[k]], f"hop {h} frame {k}"
+            if np.all(q == -100.0):
+                learning_frames[c] += 1
+            else:
+                first_real.setdefault(c, k0 + k)
+    # centre 0: first frame at 0 ms, visits at 0, 1000, 2000 ms -> the frame stamped 2000 ms (frame 80) is its last learning frame;
+    # centre 1: first frame at 500 ms -> the frame stamped 2500 ms (frame 100). 41 learning frames each instead of 81 frames of dwell.
+    assert first_real == {centres[0]: 81, centres[1]: 101}, first_real
+    assert learning_frames == {centres[0]: 41, centres[1]: 41}, learning_frames
+
+
 @pytest.mark.parametrize("n,fs", [(2048, 2_048_000), (8192, 2_048_000)])
 def test_spectrogram_payloads_byte_for_byte(n, fs):
     """Output size = min(16384, getFft(fs, 1000)) = 2048 (spectrogram.cpp:14). n = 2048: decimator factor 1; n = 8192 (the
