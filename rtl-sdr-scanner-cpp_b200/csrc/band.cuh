@@ -677,6 +677,9 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   sa.power_lin = nullptr;
   sa.peak_index = s.peak_idx.p;
   sa.peak_value = s.peak_val.p;
+  sa.zero_per_frame[0] = d_slot_count.p;  // K2's per-frame counters are zeroed by K1 (no memsets between the two kernels)
+  sa.zero_per_frame[1] = s.cand_flag.p;
+  sa.zero_scalar = s.max_count.p;
   if (profiling) CU(cudaEventRecord(s.ev[0], stream));
   if ((rc = launch_spectrum(engine, n, cfg.iq_format, sa, stream))) return rc;
   if (profiling) CU(cudaEventRecord(s.ev[1], stream));
@@ -716,9 +719,6 @@ int b2s_band::enqueue_chunk(PushSlot& s, const void* iq_dev, size_t frames, int6
   // ---- K2: noise / averager / boxcar / detect / spectrogram ----
   NoiseSlot* ns = nullptr;
   if ((rc = noise_slot(&ns))) return rc;
-  CU(cudaMemsetAsync(d_slot_count.p, 0, sizeof(int) * T, stream));
-  CU(cudaMemsetAsync(s.max_count.p, 0, sizeof(int), stream));
-  CU(cudaMemsetAsync(s.cand_flag.p, 0, sizeof(int) * T, stream));
   s.n_watch = 0;
   if (s.host_track) {  // the host tracker is helped by K2's watched-window maxima of the keys that are live now
     for (const auto& kv : tracker.signals) {

@@ -167,6 +167,10 @@ struct SpectralArgs {
   float* power_lin;             // optional [n_frames][N] |X|^2 / fs (only read by the DEBUG instantiation)
   int* peak_index;              // [n_frames]
   float* peak_value;            // [n_frames]
+  // per-frame counters of the NEXT kernel on the stream (K2's slot_count and cand_flag, its max_count scalar), zeroed here so that no
+  // memset sits between K1 and K2 on the band's stream (three tiny stream operations per push otherwise); any may be null
+  int* zero_per_frame[2];
+  int* zero_scalar;
   // ---- k_spectrum3 only ----
   int* work_counter;            // [2] {next work item, CTAs finished}: dynamic work distribution; both zero between launches
   int reserve_sms;              // SMs the persistent grid leaves free (for the band's K4, which runs beside the next push's K1)
@@ -392,6 +396,9 @@ __global__ void __launch_bounds__(N / FftPlanT<N>::E) k_spectrum(const SpectralA
       __syncthreads();
       if (tid == 0) {
         a.peak_index[frame] = red_i[0];
+        if (a.zero_per_frame[0]) a.zero_per_frame[0][frame] = 0;
+        if (a.zero_per_frame[1]) a.zero_per_frame[1][frame] = 0;
+        if (frame == 0 && a.zero_scalar) *a.zero_scalar = 0;
         a.peak_value[frame] = row_max;
       }
     }

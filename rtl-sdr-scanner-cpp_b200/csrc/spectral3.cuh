@@ -203,6 +203,11 @@ __global__ void __launch_bounds__(RA * 32) k_spectrum3(const SpectralArgs a) {
     const int frame = SPLIT ? item / S : item;
     const int c = SPLIT ? item - frame * S : 0;
     if (tid == 0) s_item[(round + 1) & 1] = atomicAdd(a.work_counter, 1);  // the item after this one (read after the next barrier)
+    if (tid == 32 && c == 0) {  // K2's per-frame counters (SpectralArgs::zero_per_frame)
+      if (a.zero_per_frame[0]) a.zero_per_frame[0][frame] = 0;
+      if (a.zero_per_frame[1]) a.zero_per_frame[1][frame] = 0;
+      if (frame == 0 && a.zero_scalar) *a.zero_scalar = 0;
+    }
     if (SPLIT) {
       // ---------------- pre-pass: y_c into the exchange buffer, laid out like pass A's input [m][b] ----------------
       if (tid < S) s_ws[tid] = a.split_ws[(tid * c) & (S - 1)];
