@@ -134,6 +134,8 @@ def test_default_config_follows_setup_chains():
     # learning: first frame k with t_k >= 2000 ms completes it (noise_learner.cpp:23)
     period = 8192 * 5 * 1000.0 / 2_048_000
     assert b2s.lib().b2s_learn_frames_from_ms(2000, period) == 101
+    assert cfg.noise_learning_ms == 2000  # NOISE_LEARNING_TIME as the reference's clock rule (config.h:24, noise_learner.cpp:23)
+    assert C.sizeof(b2s.BandConfig) % 8 == 0 and b2s.BandConfig.noise_learning_ms.offset == C.sizeof(b2s.BandConfig) - 8  # appended: older fields keep their offsets
 
 
 def test_no_gpu_means_a_loud_error_not_a_fallback():
