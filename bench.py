@@ -243,16 +243,28 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     per_thread = max(64, min(512, (1 << 23) // n))
 
-    def segment(frames):
-        return synth.make_iq_int8(n, frames, bench_tones(synth, n, frames, LEARN), seed=synth.seed_for(args.config), quiet_frames=LEARN)
+    def segment(frames, learn=LEARN):
+        return synth.make_iq_int8(n, frames, bench_tones(synth, n, frames, learn), seed=synth.seed_for(args.config), quiet_frames=learn)
 
     # one step = one bounded sample (cores x per_thread frames); K steps after W warm-ups, as the contract asks
     cfg = b2s.make_config(n, fs, learn_frames=LEARN)
     period = synth.frame_period_ms(n, fs)
-    iq = np.tile(segment(per_thread), cores)
-    frames = per_thread * cores
     L = ol.oracle()
     L.orc_bench_run.restype = C.c_double
+    # size the per-step sample so that the K timed steps end within about a minute (a probe step tells the box's speed); the share of
+    # (cheap) learning frames per chain stays what it is at full size: LEARN of 512
+    full = per_thread
+    probe = np.tile(segment(per_thread), cores)
+    t_probe = L.orc_bench_run(C.byref(cfg), probe.ctypes.data_as(C.c_void_p), per_thread * cores, period, cores)
+    if t_probe * args.steps > 60.0:
+        per_thread = max(64, int(per_thread * 60.0 / (t_probe * args.steps)))
+    if per_thread != full:
+        learn = max(8, per_thread * LEARN // full)
+        cfg = b2s.make_config(n, fs, learn_frames=learn)
+        iq = np.tile(segment(per_thread, learn), cores)
+    else:
+        iq = probe
+    frames = per_thread * cores
     times = []
     for i in range(args.warmup + args.steps):
         dt = L.orc_bench_run(C.byref(cfg), iq.ctypes.data_as(C.c_void_p), frames, period, cores)
